@@ -1,0 +1,244 @@
+// Tile intersection: per-Gaussian tile counts, an exclusive-scan, 64-bit tile|depth key emission and
+// per-tile offset encoding.  Replaces gsplat `isect_tiles` (count + emit passes) and
+// `isect_offset_encode`: SURVEY.md rows a7/a9, Appendix A7.  Integer outputs are bit-exact with the
+// oracle given the same means2d / radii / depths.
+//
+// All kernels are HBM-bound streams: count 16 B in + 4 B out per (c,n); scan 4 B in + 8 B out;
+// emit 28 B per (c,n) + 12 B per intersection; offsets 8 B per intersection + 4 B per tile.
+#include "common.cuh"
+
+namespace {
+
+constexpr int IB = 256;
+
+// tile bounding box [xmin,xmax) x [ymin,ymax) of one projected Gaussian (same op order as the oracle:
+// tile_xy = mean/tile, tile_r = radius/tile, floor(tile_xy - tile_r), ceil(tile_xy + tile_r), clamp)
+__device__ __forceinline__ bool tile_bbox(float2 m, int2 r, int tile_w, int tile_h, int& xmin, int& ymin, int& xmax,
+                                          int& ymax) {
+  if (r.x <= 0 || r.y <= 0) return false;
+  const float ts = (float)RS_TILE;
+  float tx = __fdiv_rn(m.x, ts), ty = __fdiv_rn(m.y, ts);
+  float rx = __fdiv_rn((float)r.x, ts), ry = __fdiv_rn((float)r.y, ts);
+  float fx0 = floorf(__fsub_rn(tx, rx)), fy0 = floorf(__fsub_rn(ty, ry));
+  float fx1 = ceilf(__fadd_rn(tx, rx)), fy1 = ceilf(__fadd_rn(ty, ry));
+  xmin = (int)fminf(fmaxf(fx0, 0.f), (float)tile_w);
+  ymin = (int)fminf(fmaxf(fy0, 0.f), (float)tile_h);
+  xmax = (int)fminf(fmaxf(fx1, 0.f), (float)tile_w);
+  ymax = (int)fminf(fmaxf(fy1, 0.f), (float)tile_h);
+  return true;
+}
+
+__global__ void __launch_bounds__(IB)
+isect_count_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii, long long n_elems, int tile_w,
+                   int tile_h, int32_t* __restrict__ tiles_per_gauss) {
+  const long long e = (long long)blockIdx.x * IB + threadIdx.x;
+  if (e >= n_elems) return;
+  int xmin, ymin, xmax, ymax, cnt = 0;
+  if (tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax))
+    cnt = (xmax - xmin) * (ymax - ymin);
+  tiles_per_gauss[e] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass inclusive scan int32 -> int64 with decoupled look-back.  Tile order is the order in
+// which blocks draw tickets, so every predecessor a block waits on is already resident.
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = IB * SCAN_ITEMS;
+#define ST_AGG (1ull << 62)
+#define ST_PREFIX (2ull << 62)
+#define ST_MASK (3ull << 62)
+
+__global__ void __launch_bounds__(IB)
+scan_kernel(const int32_t* __restrict__ in, long long* __restrict__ out, long long n,
+            volatile unsigned long long* status, unsigned int* ticket) {
+  __shared__ unsigned int s_tile;
+  __shared__ long long s_warp[IB / 32];
+  __shared__ long long s_excl;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const long long tile = s_tile;
+  const long long base = tile * SCAN_TILE + (long long)t * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) {
+    int4 a = __ldg(reinterpret_cast<const int4*>(in + base));
+    int4 b = __ldg(reinterpret_cast<const int4*>(in + base) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = (base + i < n) ? __ldg(in + base + i) : 0;
+  }
+  long long tsum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) tsum += v[i];
+  long long inc = tsum;  // inclusive scan of thread sums inside the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    long long o = __shfl_up_sync(RS_FULL_MASK, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  long long warp_off = 0, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < IB / 32; ++w) {
+    long long s = s_warp[w];
+    if (w < warp) warp_off += s;
+    tile_total += s;
+  }
+  if (warp == 0) {
+    if (lane == 0) status[tile] = (tile == 0 ? ST_PREFIX : ST_AGG) | (unsigned long long)tile_total;
+    long long excl = 0;
+    long long p = tile - 1;  // look back 32 predecessors at a time
+    while (p >= 0) {
+      long long q = p - lane;
+      unsigned long long s;
+      unsigned ready;
+      do {
+        s = (q >= 0) ? status[q] : ST_PREFIX;  // out-of-range lanes act as a zero prefix
+        ready = __ballot_sync(RS_FULL_MASK, (s & ST_MASK) != 0ull);
+      } while (ready != RS_FULL_MASK);
+      unsigned is_prefix = __ballot_sync(RS_FULL_MASK, (s & ST_MASK) == ST_PREFIX);
+      // nearest predecessor holding an inclusive prefix; none in this window -> take all 32 aggregates
+      int first = is_prefix ? (__ffs(is_prefix) - 1) : 31;
+      long long val = (lane <= first) ? (long long)(s & ~ST_MASK) : 0ll;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) val += __shfl_xor_sync(RS_FULL_MASK, val, d);
+      excl += val;
+      if (is_prefix) break;
+      p -= 32;
+    }
+    if (lane == 0) {
+      if (tile != 0) status[tile] = ST_PREFIX | (unsigned long long)(excl + tile_total);
+      s_excl = excl;
+    }
+  }
+  __syncthreads();
+  long long run = s_excl + warp_off + (inc - tsum);
+  long long o[SCAN_ITEMS];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) { run += v[i]; o[i] = run; }
+  if (base + SCAN_ITEMS <= n) {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i += 2)
+      *reinterpret_cast<longlong2*>(out + base + i) = make_longlong2(o[i], o[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i)
+      if (base + i < n) out[base + i] = o[i];
+  }
+}
+
+__global__ void __launch_bounds__(IB)
+isect_emit_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii,
+                  const float* __restrict__ depths, const long long* __restrict__ cum, int C, int N, int tile_w,
+                  int tile_h, int tile_bits, long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+  const long long e = (long long)blockIdx.x * IB + threadIdx.x;
+  if (e >= (long long)C * N) return;
+  int xmin, ymin, xmax, ymax;
+  if (!tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax)) return;
+  const int cnt = (xmax - xmin) * (ymax - ymin);
+  if (cnt <= 0) return;
+  long long pos = __ldg(cum + e) - cnt;
+  const long long cam = e / N;
+  const unsigned long long hi_cam = (unsigned long long)cam << (32 + tile_bits);
+  const unsigned long long dbits = (unsigned long long)__float_as_uint(__ldg(depths + e));
+  for (int y = ymin; y < ymax; ++y)
+    for (int x = xmin; x < xmax; ++x) {
+      unsigned long long tile = (unsigned long long)(y * tile_w + x);
+      isect_ids[pos] = (long long)(hi_cam | (tile << 32) | dbits);
+      flatten_ids[pos] = (int32_t)e;
+      ++pos;
+    }
+}
+
+__global__ void __launch_bounds__(IB)
+offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, int n_tiles, int tile_bits, int total,
+                     int32_t* __restrict__ offsets) {
+  const long long i = (long long)blockIdx.x * IB + threadIdx.x;
+  if (i >= M) return;
+  const unsigned long long tmask = (1ull << tile_bits) - 1ull;
+  unsigned long long k = (unsigned long long)__ldg(isect_ids + i) >> 32;
+  long long cur = (long long)(k >> tile_bits) * n_tiles + (long long)(k & tmask);
+  if (i == 0) {
+    for (long long t = 0; t <= cur; ++t) offsets[t] = 0;
+  } else {
+    unsigned long long kp = (unsigned long long)__ldg(isect_ids + i - 1) >> 32;
+    long long prev = (long long)(kp >> tile_bits) * n_tiles + (long long)(kp & tmask);
+    for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+  }
+  if (i == M - 1) {
+    for (long long t = cur + 1; t < total; ++t) offsets[t] = (int32_t)M;
+  }
+}
+
+}  // namespace
+
+static int tile_bits_for(long long n_tiles) {
+  int b = 0;
+  while (n_tiles > 0) { ++b; n_tiles >>= 1; }
+  return b;  // == Python int.bit_length(), == floor(log2(n))+1
+}
+
+extern "C" int rs_tile_bits(int tile_w, int tile_h) { return tile_bits_for((long long)tile_w * tile_h); }
+
+extern "C" int rs_isect_count(const float* means2d, const int32_t* radii, long long n_elems, int tile_w, int tile_h,
+                              int32_t* tiles_per_gauss, void* stream) {
+  if (n_elems < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
+  if (n_elems == 0) return RS_OK;
+  if (!means2d || !radii || !tiles_per_gauss) return RS_ERR_BAD_ARG;
+  isect_count_kernel<<<rs_div_up(n_elems, IB), IB, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, (const int2*)radii, n_elems, tile_w, tile_h, tiles_per_gauss);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" long long rs_cumsum_temp_bytes(long long n) {
+  long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  return 16 + 8 * (tiles > 0 ? tiles : 1);
+}
+
+// inclusive prefix sum int32 -> int64; temp is caller-owned scratch of rs_cumsum_temp_bytes(n) bytes
+extern "C" int rs_cumsum_i32_i64(const int32_t* in, long long* out, long long n, void* temp, long long temp_bytes,
+                                 void* stream) {
+  if (n < 0) return RS_ERR_BAD_ARG;
+  if (n == 0) return RS_OK;
+  if (!in || !out || !temp || temp_bytes < rs_cumsum_temp_bytes(n)) return RS_ERR_BAD_ARG;
+  long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)rs_cumsum_temp_bytes(n), (cudaStream_t)stream);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  unsigned int* ticket = (unsigned int*)temp;
+  unsigned long long* status = (unsigned long long*)((char*)temp + 16);
+  scan_kernel<<<(unsigned)tiles, IB, 0, (cudaStream_t)stream>>>(in, out, n, status, ticket);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_isect_emit(const float* means2d, const int32_t* radii, const float* depths,
+                             const long long* cum_tiles, int C, int N, int tile_w, int tile_h, long long* isect_ids,
+                             int32_t* flatten_ids, void* stream) {
+  if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
+  if ((long long)C * N >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  if (C == 0 || N == 0) return RS_OK;
+  if (!means2d || !radii || !depths || !cum_tiles || !isect_ids || !flatten_ids) return RS_ERR_BAD_ARG;
+  int tile_bits = tile_bits_for((long long)tile_w * tile_h);
+  isect_emit_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, (const int2*)radii, depths, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
+      flatten_ids);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, int tile_w, int tile_h,
+                                int32_t* offsets, void* stream) {
+  if (M < 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets) return RS_ERR_BAD_ARG;
+  if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  long long n_tiles = (long long)tile_w * tile_h;
+  long long total = n_tiles * C;
+  if (M == 0) {
+    cudaError_t e = cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)total, (cudaStream_t)stream);
+    if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+    return RS_OK;
+  }
+  if (!isect_ids) return RS_ERR_BAD_ARG;
+  offset_encode_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, (int)n_tiles,
+                                                                        tile_bits_for(n_tiles), (int)total, offsets);
+  RS_RETURN_LAST_ERROR();
+}

@@ -1,0 +1,225 @@
+// Stable LSD radix sort of (uint64 key, uint32 value) pairs on a bit range, "onesweep" style:
+// one histogram pass over the keys for all digit places, then one read + one write of the pairs per
+// 8-bit digit with a decoupled look-back across blocks for the global digit offsets.
+// Replaces the cub::DeviceRadixSort::SortPairs call inside gsplat `isect_tiles(sort=True)`
+// (SURVEY.md row a8).  Stability + ascending order make the result identical, element for element,
+// to a stable argsort of the keys, which is what the oracle does.
+//
+// HBM-bound: (8 + 24 * ceil(bits/8)) B per pair.  Block = 256 threads x 16 keys.  In-block ranking uses
+// warp match-any (one counter row per warp, no shared-memory atomics); pairs are reordered through
+// shared memory so that global writes are coalesced runs per digit.
+#include "common.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int ST = 256;            // threads per block
+constexpr int SI = 16;             // items per thread
+constexpr int STILE = ST * SI;     // 4096 pairs per block
+constexpr int SWARPS = ST / 32;
+constexpr int MAX_PASSES = 8;
+#define LB_AGG (1u << 30)
+#define LB_PREFIX (2u << 30)
+#define LB_FLAGS (3u << 30)
+#define LB_VALUE (~LB_FLAGS)
+
+struct PassInfo {
+  int shift[MAX_PASSES];
+  u32 mask[MAX_PASSES];
+  int n;
+};
+
+__global__ void __launch_bounds__(ST)
+radix_hist_kernel(const u64* __restrict__ keys, long long M, PassInfo pi, u32* __restrict__ ghist) {
+  __shared__ u32 sh[MAX_PASSES * RADIX];
+  for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += ST) sh[i] = 0;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * ST;
+  for (long long i = (long long)blockIdx.x * ST + threadIdx.x; i < M; i += stride) {
+    u64 k = __ldg(keys + i);
+#pragma unroll
+    for (int p = 0; p < MAX_PASSES; ++p)
+      if (p < pi.n) atomicAdd(&sh[p * RADIX + (u32)((k >> pi.shift[p]) & pi.mask[p])], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < pi.n * RADIX; i += ST)
+    if (sh[i]) atomicAdd(ghist + i, sh[i]);
+}
+
+// inclusive scan of one u32 per thread across the 256-thread block
+__device__ __forceinline__ u32 block_inclusive_scan(u32 v, u32* s_warp, int lane, int warp) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 o = __shfl_up_sync(RS_FULL_MASK, v, d);
+    if (lane >= d) v += o;
+  }
+  if (lane == 31) s_warp[warp] = v;
+  __syncthreads();
+  u32 off = 0;
+#pragma unroll
+  for (int w = 0; w < SWARPS; ++w)
+    if (w < warp) off += s_warp[w];
+  __syncthreads();
+  return v + off;
+}
+
+__global__ void __launch_bounds__(ST)
+radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
+                     u32* __restrict__ vout, int M, int shift, u32 mask, const u32* __restrict__ ghist,
+                     volatile u32* status, u32* ticket) {
+  __shared__ u32 s_cnt[SWARPS][RADIX];
+  __shared__ u32 s_bin_start[RADIX];
+  __shared__ int s_gbase[RADIX];
+  __shared__ u32 s_warp[SWARPS];
+  __shared__ u32 s_tile;
+  __shared__ __align__(16) u64 s_keys[STILE];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+  for (int w = 0; w < SWARPS; ++w) s_cnt[w][t] = 0;
+  __syncthreads();
+  const int tile = (int)s_tile;
+  const int tile_base = tile * STILE;
+  const int n_valid = min(STILE, M - tile_base);
+
+  // ---- load (warp-contiguous, index order = (round, lane) inside each warp's 512-pair slice)
+  u64 key[SI];
+  u32 val[SI];
+#pragma unroll
+  for (int r = 0; r < SI; ++r) {
+    const int i = warp * (32 * SI) + r * 32 + lane;
+    const bool ok = i < n_valid;
+    key[r] = ok ? __ldg(kin + tile_base + i) : ~0ull;
+    val[r] = ok ? __ldg(vin + tile_base + i) : 0u;
+  }
+  // ---- warp-local stable ranks
+  u32 pos[SI];
+  const u32 lt = rs::lanemask_lt();
+#pragma unroll
+  for (int r = 0; r < SI; ++r) {
+    const u32 d = (u32)((key[r] >> shift) & mask);
+    const u32 peers = __match_any_sync(RS_FULL_MASK, d);
+    const int leader = __ffs(peers) - 1;
+    u32 old = 0;
+    if (lane == leader) {
+      old = s_cnt[warp][d];
+      s_cnt[warp][d] = old + __popc(peers);
+    }
+    old = __shfl_sync(RS_FULL_MASK, old, leader);
+    pos[r] = old + __popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+  // ---- per digit (thread t == digit): prefix over warps, block count
+  u32 bcount = 0;
+#pragma unroll
+  for (int w = 0; w < SWARPS; ++w) {
+    u32 c = s_cnt[w][t];
+    s_cnt[w][t] = bcount;
+    bcount += c;
+  }
+  // ---- publish the block's digit count, then look back for the sum over all earlier tiles
+  volatile u32* my_status = status + (size_t)tile * RADIX + t;
+  *my_status = (tile == 0 ? LB_PREFIX : LB_AGG) | bcount;
+  const u32 gh = __ldg(ghist + t);
+  const u32 bin_incl = block_inclusive_scan(bcount, s_warp, lane, warp);
+  const u32 gh_incl = block_inclusive_scan(gh, s_warp, lane, warp);
+  u32 excl_prev = 0;
+  for (int p = tile - 1; p >= 0; --p) {
+    volatile u32* ps = status + (size_t)p * RADIX + t;
+    u32 s;
+    do { s = *ps; } while ((s & LB_FLAGS) == 0u);
+    excl_prev += s & LB_VALUE;
+    if ((s & LB_FLAGS) == LB_PREFIX) break;
+  }
+  if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
+  s_bin_start[t] = bin_incl - bcount;
+  s_gbase[t] = (int)((gh_incl - gh) + excl_prev) - (int)(bin_incl - bcount);
+  __syncthreads();
+  // ---- reorder keys through shared memory, then coalesced writes
+#pragma unroll
+  for (int r = 0; r < SI; ++r) {
+    const u32 d = (u32)((key[r] >> shift) & mask);
+    pos[r] += s_bin_start[d] + s_cnt[warp][d];
+    s_keys[pos[r]] = key[r];
+  }
+  __syncthreads();
+  int out[SI];
+#pragma unroll
+  for (int i = 0; i < SI; ++i) {
+    const int p = i * ST + t;
+    const u64 k = s_keys[p];
+    const u32 d = (u32)((k >> shift) & mask);
+    out[i] = s_gbase[d] + p;
+    if (p < n_valid) kout[out[i]] = k;
+  }
+  __syncthreads();
+  u32* s_vals = reinterpret_cast<u32*>(s_keys);
+#pragma unroll
+  for (int r = 0; r < SI; ++r) s_vals[pos[r]] = val[r];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SI; ++i) {
+    const int p = i * ST + t;
+    if (p < n_valid) vout[out[i]] = s_vals[p];
+  }
+}
+
+}  // namespace
+
+static long long sort_blocks(long long M) { return (M + STILE - 1) / STILE; }
+
+extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit) {
+  int npass = end_bit > begin_bit ? (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS : 0;
+  if (npass > MAX_PASSES) npass = MAX_PASSES;
+  long long nb = sort_blocks(M > 0 ? M : 1);
+  return (long long)MAX_PASSES * RADIX * 4 + 256 + (long long)npass * nb * RADIX * 4;
+}
+
+// Sorts M pairs by key bits [begin_bit, end_bit), stable, ascending.  Both buffer pairs are clobbered.
+// Returns 0 if the sorted pairs are in (keys_b, vals_b), 1 if they are in (keys_a, vals_a), < 0 on error.
+extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
+                             int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
+  if (M < 0 || begin_bit < 0 || end_bit > 64) return RS_ERR_BAD_ARG;
+  if (M >= (1ll << 30)) return RS_ERR_UNSUPPORTED;  // look-back words carry 30-bit counts
+  if (M == 0 || end_bit <= begin_bit) return 1;
+  const int npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+  if (npass > MAX_PASSES) return RS_ERR_BAD_ARG;
+  if (!keys_a || !vals_a || !keys_b || !vals_b || !temp || temp_bytes < rs_sort_pairs_temp_bytes(M, begin_bit, end_bit))
+    return RS_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PassInfo pi;
+  pi.n = npass;
+  for (int p = 0; p < MAX_PASSES; ++p) {
+    int sh = begin_bit + p * RADIX_BITS;
+    int nb = end_bit - sh;
+    if (nb > RADIX_BITS) nb = RADIX_BITS;
+    pi.shift[p] = p < npass ? sh : 0;
+    pi.mask[p] = p < npass ? ((1u << nb) - 1u) : 0u;
+  }
+  const long long nblocks = sort_blocks(M);
+  cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)rs_sort_pairs_temp_bytes(M, begin_bit, end_bit), st);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  u32* ghist = (u32*)temp;
+  u32* tickets = (u32*)((char*)temp + MAX_PASSES * RADIX * 4);
+  u32* status = (u32*)((char*)temp + MAX_PASSES * RADIX * 4 + 256);
+  int hist_blocks = (int)(nblocks < 148 * 8 ? nblocks : 148 * 8);
+  radix_hist_kernel<<<hist_blocks, ST, 0, st>>>((const u64*)keys_a, M, pi, ghist);
+  u64* ka = (u64*)keys_a; u64* kb = (u64*)keys_b;
+  u32* va = (u32*)vals_a; u32* vb = (u32*)vals_b;
+  for (int p = 0; p < npass; ++p) {
+    radix_scatter_kernel<<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
+                                                          ghist + p * RADIX, status + (size_t)p * nblocks * RADIX,
+                                                          tickets + p);
+    u64* tk = ka; ka = kb; kb = tk;
+    u32* tv = va; va = vb; vb = tv;
+  }
+  rs_count_launches(1 + npass);
+  e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return (npass & 1) ? 0 : 1;
+}

@@ -1,0 +1,584 @@
+// Per-tile front-to-back alpha compositing (forward) and its back-to-front gradient (backward) with the
+// RaDe-GS outputs: colours (N-D), alpha, expected ray-depth, median depth, normals.
+// Replaces gsplat-rade `rasterize_to_pixels` fwd/bwd: SURVEY.md rows a10/a11, Appendix A8/A9; reached
+// from collab_splats/models/rade_gs_model.py:439-465 and rade_features_model.py:450-476.
+//
+// Design (B200, FP32 SIMT -- compositing is not a dense contraction):
+//  * per-(camera,Gaussian) inputs are first packed into one 64-byte geometry record (+ a padded colour
+//    row), so a tile gathers each Gaussian with 16-byte cp.async copies straight into shared memory;
+//    conics are pre-scaled by log2(e) (alpha = o * 2^-sigma') and each record carries the half-extents of
+//    its alpha >= 1/255 footprint;
+//  * one CTA per 16x16 tile, 8 warps, each warp owns an 8x4 pixel block; batches are double-buffered
+//    (ids two batches ahead, records one batch ahead) so the gather overlaps the blend;
+//  * each warp ballots the batch against its own 8x4 rectangle (conservative footprint test, so the
+//    result is identical to testing every pair) and only evaluates the survivors; warps stop as soon
+//    as all 32 pixels have saturated, the CTA as soon as all warps have;
+//  * backward: the D+4 blended channels collapse to ONE suffix accumulator per pixel
+//    (w_i = <v_out, val_i>), per-Gaussian gradients are reduced across the warp with a recursive-halving
+//    shuffle tree (K-1 shuffles for K values instead of 5K) and committed with one coalesced 64-byte
+//    RED per (warp, Gaussian) into a packed gradient record.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RT = 256;  // threads per CTA (16x16 pixels)
+#define RS_LOG2E 1.4426950408889634f
+#define RS_LN2 0.6931471805599453f
+
+template <int DP> struct Batch { static constexpr int value = DP <= 8 ? 256 : (DP <= 32 ? 128 : 64); };
+
+// ------------------------------------------------------------------------------------------------ pack
+__global__ void __launch_bounds__(256)
+pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ conics,
+                 const float* __restrict__ opacities, const float* __restrict__ ray_ts,
+                 const float2* __restrict__ ray_planes, const float* __restrict__ normals,
+                 const int2* __restrict__ radii, long long n_elems, float4* __restrict__ geom) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n_elems) return;
+  float4 q0 = make_float4(0.f, 0.f, -1e30f, -1e30f), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f), q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool live = true;
+  if (radii) { int2 r = __ldg(radii + e); live = r.x > 0 && r.y > 0; }
+  if (live) {
+    float2 m = __ldg(means2d + e);
+    float a = __ldg(conics + e * 3), b = __ldg(conics + e * 3 + 1), c = __ldg(conics + e * 3 + 2);
+    float o = __ldg(opacities + e);
+    // footprint of alpha >= 1/255: sigma <= tau = ln(255 o); bbox half extents sqrt(2 tau Sigma_ii), padded
+    // so that the test can only ever keep more pairs than the exact per-pair test would
+    float hx = 1e30f, hy = 1e30f;
+    float tau = logf(255.f * o);
+    if (tau < -0.02f) {
+      hx = -1e30f; hy = -1e30f;  // alpha < 1/255 everywhere
+    } else if (tau == tau) {
+      float det = a * c - b * b;
+      if (det > 0.f && isfinite(det)) {
+        float s = 2.f * (tau + 0.03f) / det;
+        float ex = sqrtf(s * c) * 1.001f + 0.02f, ey = sqrtf(s * a) * 1.001f + 0.02f;
+        if (isfinite(ex) && isfinite(ey)) { hx = ex; hy = ey; }
+      }
+    }
+    q0 = make_float4(m.x, m.y, hx, hy);
+    q1 = make_float4(0.5f * RS_LOG2E * a, RS_LOG2E * b, 0.5f * RS_LOG2E * c, o);
+    float2 rp = __ldg(ray_planes + e);
+    q2 = make_float4(__ldg(ray_ts + e), rp.x, rp.y, 0.f);
+    q3 = make_float4(__ldg(normals + e * 3), __ldg(normals + e * 3 + 1), __ldg(normals + e * 3 + 2), 0.f);
+  }
+  geom[e * 4 + 0] = q0; geom[e * 4 + 1] = q1; geom[e * 4 + 2] = q2; geom[e * 4 + 3] = q3;
+}
+
+__global__ void __launch_bounds__(256)
+pack_colors_kernel(const float* __restrict__ colors, long long rows, int D, int DP, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * DP) return;
+  const long long r = i / DP;
+  const int k = (int)(i - r * DP);
+  out[i] = k < D ? __ldg(colors + r * D + k) : 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+unpack_geom_grad_kernel(const float4* __restrict__ gg, long long n_elems, float2* __restrict__ v_means2d,
+                        float2* __restrict__ v_means2d_abs, float* __restrict__ v_conics,
+                        float* __restrict__ v_opacities, float* __restrict__ v_ray_ts,
+                        float2* __restrict__ v_ray_planes, float* __restrict__ v_normals) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n_elems) return;
+  float4 g0 = gg[e * 4], g1 = gg[e * 4 + 1], g2 = gg[e * 4 + 2], g3 = gg[e * 4 + 3];
+  v_means2d[e] = make_float2(g0.x, g0.y);
+  if (v_means2d_abs) v_means2d_abs[e] = make_float2(g0.z, g0.w);
+  v_conics[e * 3] = g1.x; v_conics[e * 3 + 1] = g1.y; v_conics[e * 3 + 2] = g1.z;
+  v_opacities[e] = g1.w;
+  v_ray_ts[e] = g2.x;
+  v_ray_planes[e] = make_float2(g2.y, g2.z);
+  v_normals[e * 3] = g3.x; v_normals[e * 3 + 1] = g3.y; v_normals[e * 3 + 2] = g3.z;
+}
+
+__global__ void __launch_bounds__(256)
+unpack_colors_grad_kernel(const float* __restrict__ cg, long long rows, int D, int DP, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= rows * D) return;
+  const long long r = i / D;
+  const int k = (int)(i - r * D);
+  out[i] = cg[r * DP + k];
+}
+
+// ------------------------------------------------------------------------------------------------ shared
+struct RasterArgs {
+  const float4* geom;        // [C*N][4]
+  const float* colors;       // [color_rows][DP]
+  const float* backgrounds;  // [C][D] or null
+  const float* Ks;           // [C][9]
+  int C, N, W, H, tile_w, tile_h, D, color_per_cam;
+  const int* offsets;        // [C*tile_h*tile_w]
+  const int* flatten_ids;    // [M]
+  int M;
+  // forward outputs == backward saved tensors
+  float* out_colors;   // [C,H,W,D]
+  float* out_alphas;   // [C,H,W]
+  float* out_dexp;     // [C,H,W]
+  float* out_dmed;     // [C,H,W]
+  float* out_normals;  // [C,H,W,3]
+  float* out_T;        // [C,H,W]   final transmittance
+  int* last_ids;       // [C,H,W]
+  int* median_ids;     // [C,H,W]
+  // backward inputs / outputs
+  const float* v_colors; const float* v_alphas; const float* v_dexp; const float* v_dmed; const float* v_normals;
+  float* geom_grad;    // [C*N][16]
+  float* color_grad;   // [color_rows][DP]
+};
+
+template <int DP, int BATCH> struct Smem {
+  float4 q0[2][BATCH], q1[2][BATCH], q2[2][BATCH], q3[2][BATCH];
+  float col[2][BATCH][DP];
+  int ids[2][BATCH];
+  int red[8];
+};
+
+// gather one batch (ids already in s.ids[buf]) with 16-byte cp.async copies; consecutive threads copy
+// consecutive 16-byte chunks of one record, so each 64-byte record is one coalesced request
+template <int DP, int BATCH>
+__device__ __forceinline__ void issue_gather(Smem<DP, BATCH>& s, int buf, int count, const RasterArgs& a, int t) {
+  constexpr int CH = 4 + DP / 4;
+  const int total = count * CH;
+  for (int i = t; i < total; i += RT) {
+    const int slot = i / CH, ch = i - slot * CH;
+    const int id = s.ids[buf][slot];
+    if (ch < 4) {
+      float4* dst = (ch == 0 ? s.q0[buf] : ch == 1 ? s.q1[buf] : ch == 2 ? s.q2[buf] : s.q3[buf]) + slot;
+      rs::cp_async16(dst, a.geom + (size_t)id * 4 + ch);
+    } else {
+      const int row = a.color_per_cam ? id : id % a.N;
+      rs::cp_async16(&s.col[buf][slot][(ch - 4) * 4], a.colors + (size_t)row * DP + (ch - 4) * 4);
+    }
+  }
+  rs::cp_async_commit();
+}
+
+struct TileCtx {
+  int cam, start, end, x0, y0, pxi, pyi;
+  bool inside;
+  float px, py, rcx, rcy;
+};
+
+__device__ __forceinline__ TileCtx tile_ctx(const RasterArgs& a, int lane, int warp) {
+  TileCtx c;
+  const int tile_id = blockIdx.x;
+  const int tiles_per_cam = a.tile_w * a.tile_h;
+  c.cam = tile_id / tiles_per_cam;
+  const int tl = tile_id - c.cam * tiles_per_cam;
+  const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
+  c.start = __ldg(a.offsets + tile_id);
+  c.end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  c.x0 = txi * RS_TILE + (warp & 1) * 8;
+  c.y0 = tyi * RS_TILE + (warp >> 1) * 4;
+  c.pxi = c.x0 + (lane & 7);
+  c.pyi = c.y0 + (lane >> 3);
+  c.inside = c.pxi < a.W && c.pyi < a.H;
+  c.px = c.pxi + 0.5f; c.py = c.pyi + 0.5f;
+  c.rcx = c.x0 + 4.0f; c.rcy = c.y0 + 2.0f;
+  return c;
+}
+
+// 1 / sqrt(((px-cx)/fx)^2 + ((py-cy)/fy)^2 + 1): ray distance -> z depth
+__device__ __forceinline__ float inv_ray_len(const RasterArgs& a, int cam, float px, float py) {
+  const float* K = a.Ks + (size_t)cam * 9;
+  const float fx = __ldg(K), fy = __ldg(K + 4), cx = __ldg(K + 2), cy = __ldg(K + 5);
+  const float rx = (px - cx) / fx, ry = (py - cy) / fy;
+  return 1.0f / sqrtf(rx * rx + ry * ry + 1.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int DP, int BATCH>
+__global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const TileCtx c = tile_ctx(a, lane, warp);
+  const int start = c.start, end = c.end;
+  const float px = c.px, py = c.py;
+
+  float T = 1.f, dsum = 0.f, tmed = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  float acc[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) acc[k] = 0.f;
+  int last_id = start - 1, med_id = -1;
+  bool done = !c.inside;
+
+  const int nb = (end - start + BATCH - 1) / BATCH;
+  if (nb > 0) {
+    if (t < BATCH) { const int i = start + t; s.ids[0][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH>(s, 0, min(BATCH, end - start), a, t);
+    if (nb > 1 && t < BATCH) { const int i = start + BATCH + t; s.ids[1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+  }
+  bool warp_done = __all_sync(RS_FULL_MASK, done);
+  for (int b = 0; b < nb; ++b) {
+    rs::cp_async_wait_all();
+    // barrier: batch b has landed, ids[(b+1)&1] are visible, every warp has finished batch b-1
+    if (__syncthreads_count(!done) == 0) break;
+    int next_id = 0;
+    if (b + 1 < nb) {
+      issue_gather<DP, BATCH>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
+      if (b + 2 < nb && t < BATCH) {
+        const int i = start + (b + 2) * BATCH + t;
+        next_id = i < end ? __ldg(a.flatten_ids + i) : 0;
+      }
+    }
+    if (!warp_done) {
+      const int buf = b & 1;
+      const int base_idx = start + b * BATCH;
+      const int bcount = min(BATCH, end - base_idx);
+      for (int g0 = 0; g0 < bcount; g0 += 32) {
+        const int j = g0 + lane;
+        bool hit = false;
+        if (j < bcount) {
+          const float4 f = s.q0[buf][j];
+          hit = fabsf(f.x - c.rcx) <= f.z + 3.5f && fabsf(f.y - c.rcy) <= f.w + 1.5f;
+        }
+        unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+        while (m) {
+          const int jj = g0 + __ffs(m) - 1;
+          m &= m - 1;
+          const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
+          const float dx = q0.x - px, dy = q0.y - py;
+          const float sig = q1.x * dx * dx + q1.z * dy * dy + q1.y * dx * dy;
+          const float alpha = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
+          if (!done && sig >= 0.f && alpha >= RS_ALPHA_MIN) {
+            const float nT = T * (1.f - alpha);
+            if (nT <= RS_T_STOP) {
+              done = true;
+            } else {
+              const float vis = alpha * T;
+              const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+              const float tt = q2.x + q2.y * dx + q2.z * dy;
+              dsum += vis * tt;
+              nx += vis * q3.x; ny += vis * q3.y; nz += vis * q3.z;
+              const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+#pragma unroll
+              for (int k = 0; k < DP / 4; ++k) {
+                const float4 cc = cp[k];
+                acc[4 * k] += vis * cc.x; acc[4 * k + 1] += vis * cc.y;
+                acc[4 * k + 2] += vis * cc.z; acc[4 * k + 3] += vis * cc.w;
+              }
+#if RS_MEDIAN_INCLUSIVE
+              if (T > 0.5f && nT <= 0.5f) { tmed = tt; med_id = base_idx + jj; }
+#else
+              if (T > 0.5f && nT < 0.5f) { tmed = tt; med_id = base_idx + jj; }
+#endif
+              last_id = base_idx + jj;
+              T = nT;
+            }
+          }
+          if (__all_sync(RS_FULL_MASK, done)) { warp_done = true; break; }
+        }
+        if (warp_done) break;
+      }
+    }
+    if (b + 2 < nb && t < BATCH) s.ids[b & 1][t] = next_id;  // batch b's ids are dead (gather issued last iteration)
+  }
+  rs::cp_async_wait_all();
+
+  if (c.inside) {
+    const size_t pix = ((size_t)c.cam * a.H + c.pyi) * a.W + c.pxi;
+    const float il = inv_ray_len(a, c.cam, px, py);
+    float* oc = a.out_colors + pix * a.D;
+    const float* bg = a.backgrounds ? a.backgrounds + (size_t)c.cam * a.D : nullptr;
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+      if (k < a.D) oc[k] = acc[k] + (bg ? T * __ldg(bg + k) : 0.f);
+    a.out_alphas[pix] = 1.f - T;
+    a.out_T[pix] = T;
+#if RS_NORMALIZE_EXPECTED_DEPTH
+    a.out_dexp[pix] = dsum * il / fmaxf(1.f - T, 1e-10f);
+#else
+    a.out_dexp[pix] = dsum * il;
+#endif
+    a.out_dmed[pix] = tmed * il;
+    a.out_normals[pix * 3] = nx; a.out_normals[pix * 3 + 1] = ny; a.out_normals[pix * 3 + 2] = nz;
+    a.last_ids[pix] = last_id;
+    a.median_ids[pix] = med_id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// reduce-and-commit the DP colour gradients in power-of-two chunks
+template <int DP, int OFF>
+__device__ __forceinline__ void commit_color_grads(const float (&v_c)[DP], float vis, float* __restrict__ dst, int D,
+                                                   int lane) {
+  if constexpr (OFF < DP) {
+    constexpr int REM = DP - OFF;
+    constexpr int K = REM >= 32 ? 32 : REM >= 16 ? 16 : REM >= 8 ? 8 : 4;
+    float cv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) cv[k] = vis * v_c[OFF + k];
+    rs::warp_reduce_scatter<K>(cv, lane);
+    constexpr int GROUP = 32 / K;
+    const int slot = OFF + lane / GROUP;
+    if ((lane % GROUP) == 0 && slot < D) atomicAdd(dst + slot, cv[0]);
+    commit_color_grads<DP, OFF + K>(v_c, vis, dst, D, lane);
+  }
+}
+
+template <int DP, int BATCH>
+__global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const TileCtx c = tile_ctx(a, lane, warp);
+  const int start = c.start, end = c.end;
+  const float px = c.px, py = c.py;
+  const bool inside = c.inside;
+  const size_t pix = inside ? ((size_t)c.cam * a.H + c.pyi) * a.W + c.pxi : 0;
+
+  float v_c[DP];
+#pragma unroll
+  for (int k = 0; k < DP; ++k) v_c[k] = (inside && k < a.D) ? __ldg(a.v_colors + pix * a.D + k) : 0.f;
+  const float T_final = inside ? a.out_T[pix] : 1.f;
+  const int last_id = inside ? a.last_ids[pix] : start - 1;
+  const int med_id = inside ? a.median_ids[pix] : -1;
+  const float il = inside ? inv_ray_len(a, c.cam, px, py) : 0.f;
+#if RS_NORMALIZE_EXPECTED_DEPTH
+#error "alpha-normalised expected depth (Q1) needs the extra dDexp/dalpha term in the backward"
+#endif
+  const float v_dsum = inside ? __ldg(a.v_dexp + pix) * il : 0.f;
+  const float v_dmed = inside ? __ldg(a.v_dmed + pix) * il : 0.f;
+  const float v_n0 = inside ? __ldg(a.v_normals + pix * 3) : 0.f;
+  const float v_n1 = inside ? __ldg(a.v_normals + pix * 3 + 1) : 0.f;
+  const float v_n2 = inside ? __ldg(a.v_normals + pix * 3 + 2) : 0.f;
+  float bgdot = 0.f;
+  if (a.backgrounds) {
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+      if (k < a.D) bgdot += __ldg(a.backgrounds + (size_t)c.cam * a.D + k) * v_c[k];
+  }
+  const float tfin_term = inside ? T_final * (__ldg(a.v_alphas + pix) - bgdot) : 0.f;
+  float T = T_final, R = 0.f;
+
+  // warp / CTA extent of the lists
+  int warp_last = last_id;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(RS_FULL_MASK, warp_last, d));
+  if (lane == 0) s.red[warp] = warp_last;
+  __syncthreads();
+  int blk_last = start - 1;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) blk_last = max(blk_last, s.red[w]);
+  const int nb = blk_last >= start ? (blk_last - start) / BATCH + 1 : 0;
+
+  if (nb > 0) {
+    const int bl = nb - 1;
+    if (t < BATCH) { const int i = start + bl * BATCH + t; s.ids[bl & 1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
+    if (bl >= 1 && t < BATCH) s.ids[(bl - 1) & 1][t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + t);
+  }
+  for (int b = nb - 1; b >= 0; --b) {
+    rs::cp_async_wait_all();
+    __syncthreads();
+    int next_id = 0;
+    if (b >= 1) {
+      issue_gather<DP, BATCH>(s, (b - 1) & 1, BATCH, a, t);
+      if (b >= 2 && t < BATCH) next_id = __ldg(a.flatten_ids + start + (b - 2) * BATCH + t);
+    }
+    const int buf = b & 1;
+    const int base_idx = start + b * BATCH;
+    const int hi = min(min(BATCH, end - base_idx) - 1, warp_last - base_idx);
+    for (int g0 = hi >= 0 ? (hi & ~31) : -32; g0 >= 0; g0 -= 32) {
+      const int j = g0 + lane;
+      bool hit = false;
+      if (j <= hi) {
+        const float4 f = s.q0[buf][j];
+        hit = fabsf(f.x - c.rcx) <= f.z + 3.5f && fabsf(f.y - c.rcy) <= f.w + 1.5f;
+      }
+      unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+      while (m) {
+        const int bit = 31 - __clz(m);
+        m &= ~(1u << bit);
+        const int jj = g0 + bit;
+        const int idx = base_idx + jj;
+        const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
+        const float dx = q0.x - px, dy = q0.y - py;
+        const float sig = q1.x * dx * dx + q1.z * dy * dy + q1.y * dx * dy;
+        const float ex = rs::fast_exp2(-sig);
+        const float oe = q1.w * ex;
+        const float alpha = fminf(RS_ALPHA_MAX, oe);
+        const bool valid = inside && idx <= last_id && sig >= 0.f && alpha >= RS_ALPHA_MIN;
+        if (!__any_sync(RS_FULL_MASK, valid)) continue;
+        const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+        float gq[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gq[k] = 0.f;
+        float vis = 0.f;
+        if (valid) {
+          const float ra = __frcp_rn(1.f - alpha);
+          T *= ra;  // transmittance in front of this Gaussian
+          vis = alpha * T;
+          const float tt = q2.x + q2.y * dx + q2.z * dy;
+          float w = v_dsum * tt + v_n0 * q3.x + v_n1 * q3.y + v_n2 * q3.z;
+          const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+#pragma unroll
+          for (int k = 0; k < DP / 4; ++k) {
+            const float4 cc = cp[k];
+            w += v_c[4 * k] * cc.x + v_c[4 * k + 1] * cc.y + v_c[4 * k + 2] * cc.z + v_c[4 * k + 3] * cc.w;
+          }
+          const float v_alpha = T * w - R * ra + tfin_term * ra;
+          R += vis * w;
+          const float v_t = vis * v_dsum + (idx == med_id ? v_dmed : 0.f);
+          float v_sig = 0.f, v_o = 0.f;
+          if (oe <= RS_ALPHA_MAX) { v_sig = -alpha * v_alpha; v_o = ex * v_alpha; }
+          // d sigma / d(dx,dy) with the raw conic (a,b,c) = ln2 * (2 q1.x, q1.y, 2 q1.z)
+          const float gx = v_sig * RS_LN2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
+          const float gy = v_sig * RS_LN2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
+          gq[0] = gx; gq[1] = gy; gq[2] = fabsf(gx); gq[3] = fabsf(gy);
+          gq[4] = 0.5f * dx * dx * v_sig; gq[5] = dx * dy * v_sig; gq[6] = 0.5f * dy * dy * v_sig; gq[7] = v_o;
+          gq[8] = v_t; gq[9] = v_t * dx; gq[10] = v_t * dy;
+          gq[12] = vis * v_n0; gq[13] = vis * v_n1; gq[14] = vis * v_n2;
+        }
+        const int id = s.ids[buf][jj];  // still batch b's ids: the slot is only recycled after this blend
+        rs::warp_reduce_scatter<16>(gq, lane);
+        {
+          const int slot = lane >> 1;
+          if ((lane & 1) == 0 && slot != 11 && slot != 15) atomicAdd(a.geom_grad + (size_t)id * 16 + slot, gq[0]);
+        }
+        const int row = a.color_per_cam ? id : id % a.N;
+        commit_color_grads<DP, 0>(v_c, vis, a.color_grad + (size_t)row * DP, a.D, lane);
+      }
+    }
+    if (b >= 2 && t < BATCH) s.ids[b & 1][t] = next_id;
+  }
+  rs::cp_async_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
+  constexpr int B = Batch<DP>::value;
+  const size_t smem = sizeof(Smem<DP, B>);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_fwd_kernel<DP, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  rasterize_fwd_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  RS_RETURN_LAST_ERROR();
+}
+template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
+  constexpr int B = Batch<DP>::value;
+  const size_t smem = sizeof(Smem<DP, B>);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  rasterize_bwd_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  RS_RETURN_LAST_ERROR();
+}
+
+#define RS_DP_LIST(X) X(4) X(8) X(16) X(20) X(32) X(36) X(64) X(68) X(72)
+
+int padded_channels(int D) {
+  const int list[] = {4, 8, 16, 20, 32, 36, 64, 68, 72};
+  for (int v : list)
+    if (D <= v) return v;
+  return -1;
+}
+
+bool check_common(const RasterArgs& a) {
+  return a.C > 0 && a.N > 0 && a.W > 0 && a.H > 0 && a.tile_w > 0 && a.tile_h > 0 && a.D > 0 && a.M >= 0 && a.geom &&
+         a.colors && a.Ks && a.offsets && (a.M == 0 || a.flatten_ids) && a.out_T && a.last_ids && a.median_ids;
+}
+
+}  // namespace
+
+extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
+
+extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, const float* ray_ts,
+                            const float* ray_planes, const float* normals, const int32_t* radii, long long n_elems,
+                            float* geom, void* stream) {
+  if (n_elems < 0) return RS_ERR_BAD_ARG;
+  if (n_elems == 0) return RS_OK;
+  if (!means2d || !conics || !opacities || !ray_ts || !ray_planes || !normals || !geom) return RS_ERR_BAD_ARG;
+  pack_geom_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, conics, opacities, ray_ts, (const float2*)ray_planes, normals, (const int2*)radii,
+      n_elems, (float4*)geom);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_pack_colors(const float* colors, long long rows, int D, int DP, float* out, void* stream) {
+  if (rows < 0 || D <= 0 || DP < D) return RS_ERR_BAD_ARG;
+  if (rows == 0) return RS_OK;
+  if (!colors || !out) return RS_ERR_BAD_ARG;
+  pack_colors_kernel<<<rs_div_up(rows * DP, 256), 256, 0, (cudaStream_t)stream>>>(colors, rows, D, DP, out);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_unpack_geom_grad(const float* geom_grad, long long n_elems, float* v_means2d, float* v_means2d_abs,
+                                   float* v_conics, float* v_opacities, float* v_ray_ts, float* v_ray_planes,
+                                   float* v_normals, void* stream) {
+  if (n_elems < 0) return RS_ERR_BAD_ARG;
+  if (n_elems == 0) return RS_OK;
+  if (!geom_grad || !v_means2d || !v_conics || !v_opacities || !v_ray_ts || !v_ray_planes || !v_normals)
+    return RS_ERR_BAD_ARG;
+  unpack_geom_grad_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)geom_grad, n_elems, (float2*)v_means2d, (float2*)v_means2d_abs, v_conics, v_opacities, v_ray_ts,
+      (float2*)v_ray_planes, v_normals);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_unpack_colors_grad(const float* color_grad, long long rows, int D, int DP, float* out, void* stream) {
+  if (rows < 0 || D <= 0 || DP < D) return RS_ERR_BAD_ARG;
+  if (rows == 0) return RS_OK;
+  if (!color_grad || !out) return RS_ERR_BAD_ARG;
+  unpack_colors_grad_kernel<<<rs_div_up(rows * D, 256), 256, 0, (cudaStream_t)stream>>>(color_grad, rows, D, DP, out);
+  RS_RETURN_LAST_ERROR();
+}
+
+extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+                                const float* backgrounds, const float* Ks, int C, int N, int width, int height,
+                                int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                long long M, float* out_colors, float* out_alphas, float* out_expected_depths,
+                                float* out_median_depths, float* out_normals, float* out_transmittance,
+                                int32_t* last_ids, int32_t* median_ids, void* stream) {
+  if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  RasterArgs a{};
+  a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;
+  a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
+  a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
+  a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
+  a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
+  a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
+  if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
+    return RS_ERR_BAD_ARG;
+  if (tile_w != rs_div_up(width, RS_TILE) || tile_h != rs_div_up(height, RS_TILE)) return RS_ERR_BAD_ARG;
+  const int DP = padded_channels(D);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (DP) {
+#define X(v) case v: return launch_fwd<v>(a, st);
+    RS_DP_LIST(X)
+#undef X
+    default: return RS_ERR_UNSUPPORTED;
+  }
+}
+
+extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+                                const float* backgrounds, const float* Ks, int C, int N, int width, int height,
+                                int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                                long long M, const float* transmittance, const int32_t* last_ids,
+                                const int32_t* median_ids, const float* v_colors, const float* v_alphas,
+                                const float* v_expected_depths, const float* v_median_depths, const float* v_normals,
+                                float* geom_grad, float* color_grad, void* stream) {
+  if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  RasterArgs a{};
+  a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;
+  a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
+  a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
+  a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
+  a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;
+  a.v_colors = v_colors; a.v_alphas = v_alphas; a.v_dexp = v_expected_depths; a.v_dmed = v_median_depths;
+  a.v_normals = v_normals; a.geom_grad = geom_grad; a.color_grad = color_grad;
+  if (!check_common(a) || !v_colors || !v_alphas || !v_expected_depths || !v_median_depths || !v_normals ||
+      !geom_grad || !color_grad)
+    return RS_ERR_BAD_ARG;
+  if (tile_w != rs_div_up(width, RS_TILE) || tile_h != rs_div_up(height, RS_TILE)) return RS_ERR_BAD_ARG;
+  if (M == 0) return RS_OK;
+  const int DP = padded_channels(D);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (DP) {
+#define X(v) case v: return launch_bwd<v>(a, st);
+    RS_DP_LIST(X)
+#undef X
+    default: return RS_ERR_UNSUPPORTED;
+  }
+}

@@ -1,0 +1,413 @@
+"""Stage-wise operators with the names and argument meaning of ``gsplat.cuda._wrapper``.
+
+collab-splats imports ``fully_fused_projection`` (collab_splats/models/rade_gs_model.py:20, called at
+:373-389) and ``spherical_harmonics`` (collab_splats/models/rade_features_model.py:20, called at :430-434)
+from this module; ``isect_tiles``, ``isect_offset_encode`` and ``rasterize_to_pixels`` are what
+``gsplat.rendering.rasterization`` is made of.
+
+Every operator is a thin ``torch.autograd.Function`` around the C ABI of librade_b200.so
+(include/rade_b200.h) -- torch only owns device memory and the stream.  Options of upstream gsplat that
+collab-splats never uses (packed=True, sparse_grad, covars, non-pinhole cameras, 2DGS ...) raise
+``NotImplementedError``; nothing silently falls back.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from radegs_b200 import backend as _be
+
+TILE_SIZE = 16
+
+
+def _c(t: Optional[Tensor], dtype=torch.float32) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gsplat (B200 build): tensors must live on a CUDA device; there is no CPU path")
+
+
+# ------------------------------------------------------------------------------------------------ projection
+class _FullyFusedProjection(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, calc_compensations):
+        lib = _be.load()
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        radii = torch.empty(C, N, 2, device=dev, dtype=torch.int32)
+        means2d = torch.empty(C, N, 2, **f32)
+        depths = torch.empty(C, N, **f32)
+        conics = torch.empty(C, N, 3, **f32)
+        comps = torch.empty(C, N, **f32) if calc_compensations else None
+        ray_ts = torch.empty(C, N, **f32)
+        ray_planes = torch.empty(C, N, 2, **f32)
+        normals = torch.empty(C, N, 3, **f32)
+        with torch.cuda.device(dev):
+            _be.check(lib.rs_project_fwd(
+                _be.ptr(means), _be.ptr(quats), _be.ptr(scales), _be.ptr(viewmats), _be.ptr(Ks), C, N, width, height,
+                eps2d, near_plane, far_plane, radius_clip, int(calc_compensations), _be.ptr(radii), _be.ptr(means2d),
+                _be.ptr(depths), _be.ptr(conics), _be.ptr(comps), _be.ptr(ray_ts), _be.ptr(ray_planes),
+                _be.ptr(normals), _be.stream_ptr(dev)), "rs_project_fwd")
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks)
+        ctx.cfg = (width, height, eps2d, near_plane, far_plane, radius_clip, calc_compensations)
+        ctx.mark_non_differentiable(radii)
+        if comps is None:
+            return radii, means2d, depths, conics, ray_ts, ray_planes, normals
+        return radii, means2d, depths, conics, comps, ray_ts, ray_planes, normals
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _be.load()
+        means, quats, scales, viewmats, Ks = ctx.saved_tensors
+        width, height, eps2d, near_plane, far_plane, radius_clip, calc_comp = ctx.cfg
+        if calc_comp:
+            _, v_means2d, v_depths, v_conics, v_comps, v_ray_ts, v_ray_planes, v_normals = grads
+        else:
+            _, v_means2d, v_depths, v_conics, v_ray_ts, v_ray_planes, v_normals = grads
+            v_comps = None
+        C, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        if v_means2d is None:
+            v_means2d = torch.zeros(C, N, 2, device=dev)
+        if v_conics is None:
+            v_conics = torch.zeros(C, N, 3, device=dev)
+        v_means = torch.empty_like(means)
+        v_quats = torch.empty_like(quats)
+        v_scales = torch.empty_like(scales)
+        v_viewmats = torch.empty_like(viewmats) if ctx.needs_input_grad[3] else None
+        with torch.cuda.device(dev):
+            _be.check(lib.rs_project_bwd(
+                _be.ptr(means), _be.ptr(quats), _be.ptr(scales), _be.ptr(viewmats), _be.ptr(Ks), C, N, width, height,
+                eps2d, near_plane, far_plane, radius_clip, _be.ptr(_c(v_means2d)), _be.ptr(_c(v_depths)),
+                _be.ptr(_c(v_conics)), _be.ptr(_c(v_comps)), _be.ptr(_c(v_ray_ts)), _be.ptr(_c(v_ray_planes)),
+                _be.ptr(_c(v_normals)), _be.ptr(v_means), _be.ptr(v_quats), _be.ptr(v_scales), _be.ptr(v_viewmats),
+                _be.stream_ptr(dev)), "rs_project_bwd")
+        return (v_means, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None, None)
+
+
+def fully_fused_projection(
+    means: Tensor,                 # [N,3]
+    covars: Optional[Tensor],      # must be None (quats/scales path only)
+    quats: Optional[Tensor],       # [N,4] wxyz
+    scales: Optional[Tensor],      # [N,3]
+    viewmats: Tensor,              # [C,4,4]
+    Ks: Tensor,                    # [C,3,3]
+    width: int,
+    height: int,
+    eps2d: float = 0.3,
+    near_plane: float = 0.01,
+    far_plane: float = 1e10,
+    radius_clip: float = 0.0,
+    packed: bool = False,
+    sparse_grad: bool = False,
+    calc_compensations: bool = False,
+    camera_model: str = "pinhole",
+    opacities: Optional[Tensor] = None,
+):
+    """Same call as gsplat-rade ``fully_fused_projection`` (rade_gs_model.py:373-389).  Returns the 8-tuple
+    ``radii [C,N,2] i32, means2d [C,N,2], depths [C,N], conics [C,N,3], compensations [C,N]|None,
+    ray_ts [C,N], ray_planes [C,N,2], normals [C,N,3]`` the reference unpacks at rade_gs_model.py:392-394."""
+    if covars is not None:
+        raise NotImplementedError("covars input is not on the collab-splats path; pass quats and scales")
+    if packed or sparse_grad:
+        raise NotImplementedError("packed=True / sparse_grad=True are not on the collab-splats path")
+    if camera_model != "pinhole":
+        raise NotImplementedError("only pinhole cameras are on the collab-splats path")
+    if opacities is not None:
+        raise NotImplementedError("opacity-aware radii are not used by the reference (rade_gs_model.py:373-389)")
+    if quats is None or scales is None:
+        raise ValueError("quats and scales are required")
+    N, C = means.shape[0], viewmats.shape[0]
+    assert means.shape == (N, 3), means.shape
+    assert quats.shape == (N, 4), quats.shape
+    assert scales.shape == (N, 3), scales.shape
+    assert viewmats.shape == (C, 4, 4), viewmats.shape
+    assert Ks.shape == (C, 3, 3), Ks.shape
+    _need_cuda(means, quats, scales, viewmats, Ks)
+    out = _FullyFusedProjection.apply(_c(means), _c(quats), _c(scales), _c(viewmats), _c(Ks), int(width), int(height),
+                                      float(eps2d), float(near_plane), float(far_plane), float(radius_clip),
+                                      bool(calc_compensations))
+    if calc_compensations:
+        return out
+    radii, means2d, depths, conics, ray_ts, ray_planes, normals = out
+    return radii, means2d, depths, conics, None, ray_ts, ray_planes, normals
+
+
+# ------------------------------------------------------------------------------------------------ SH
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, degree, dirs, coeffs, masks):
+        lib = _be.load()
+        K = coeffs.shape[-2]
+        n_elems = dirs.numel() // 3
+        n_rows = coeffs.numel() // (K * 3)
+        colors = torch.empty(dirs.shape, device=dirs.device, dtype=torch.float32)
+        m8 = None if masks is None else masks.to(torch.uint8).contiguous()
+        with torch.cuda.device(dirs.device):
+            _be.check(lib.rs_sh_fwd(degree, K, n_elems, n_rows, _be.ptr(dirs), _be.ptr(coeffs), _be.ptr(m8),
+                                    _be.ptr(colors), _be.stream_ptr(dirs.device)), "rs_sh_fwd")
+        ctx.save_for_backward(dirs, coeffs, m8)
+        ctx.degree = degree
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        lib = _be.load()
+        dirs, coeffs, m8 = ctx.saved_tensors
+        K = coeffs.shape[-2]
+        n_elems = dirs.numel() // 3
+        n_rows = coeffs.numel() // (K * 3)
+        v_coeffs = torch.empty_like(coeffs)
+        v_dirs = torch.empty_like(dirs) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(dirs.device):
+            _be.check(lib.rs_sh_bwd(ctx.degree, K, n_elems, n_rows, _be.ptr(dirs), _be.ptr(coeffs), _be.ptr(m8),
+                                    _be.ptr(_c(v_colors)), _be.ptr(v_coeffs), _be.ptr(v_dirs),
+                                    _be.stream_ptr(dirs.device)), "rs_sh_bwd")
+        return None, v_dirs, v_coeffs, None
+
+
+def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
+    """Same call as gsplat ``spherical_harmonics`` (rade_features_model.py:430-434): dirs [...,3],
+    coeffs [...,K,3] -> colours [...,3].  Extension: coeffs may drop the leading camera axis
+    (dirs [C,N,3], coeffs [N,K,3]) so shared coefficients are not expanded per camera."""
+    assert dirs.shape[-1] == 3 and coeffs.shape[-1] == 3, (dirs.shape, coeffs.shape)
+    K = coeffs.shape[-2]
+    if not 0 <= degrees_to_use <= 3:
+        raise NotImplementedError("SH degree must be 0..3 (the reference uses <= 3)")
+    assert (degrees_to_use + 1) ** 2 <= K <= 16, (degrees_to_use, K)
+    if coeffs.shape[:-2] != dirs.shape[:-1]:
+        assert coeffs.dim() == 3 and dirs.dim() == 3 and coeffs.shape[0] == dirs.shape[1], (dirs.shape, coeffs.shape)
+    if masks is not None:
+        assert masks.shape == dirs.shape[:-1], masks.shape
+    _need_cuda(dirs, coeffs, masks)
+    return _SphericalHarmonics.apply(int(degrees_to_use), _c(dirs), _c(coeffs), masks)
+
+
+# ------------------------------------------------------------------------------------------------ isect
+@torch.no_grad()
+def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int, tile_height: int,
+                sort: bool = True, packed: bool = False, n_cameras: Optional[int] = None,
+                camera_ids: Optional[Tensor] = None, gaussian_ids: Optional[Tensor] = None
+                ) -> Tuple[Tensor, Tensor, Tensor]:
+    """Same call as gsplat ``isect_tiles``: -> tiles_per_gauss [C,N] i32, isect_ids [M] i64 (sorted),
+    flatten_ids [M] i32.  One device->host read of M (the output size is data dependent)."""
+    if packed:
+        raise NotImplementedError("packed=True is not on the collab-splats path")
+    if tile_size != TILE_SIZE:
+        raise NotImplementedError("tile_size must be 16")
+    lib = _be.load()
+    C, N = depths.shape
+    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
+    _need_cuda(means2d, radii, depths)
+    dev = means2d.device
+    means2d, depths = _c(means2d), _c(depths)
+    radii = _c(radii, torch.int32)
+    n_elems = C * N
+    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
+    cum = torch.empty(max(n_elems, 1), device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        st = _be.stream_ptr(dev)
+        _be.check(lib.rs_isect_count(_be.ptr(means2d), _be.ptr(radii), n_elems, tile_width, tile_height,
+                                     _be.ptr(tiles), st), "rs_isect_count")
+        tb = lib.rs_cumsum_temp_bytes(n_elems)
+        temp = torch.empty(tb, device=dev, dtype=torch.uint8)
+        _be.check(lib.rs_cumsum_i32_i64(_be.ptr(tiles), _be.ptr(cum), n_elems, _be.ptr(temp), tb, st),
+                  "rs_cumsum_i32_i64")
+        M = int(cum[n_elems - 1].item()) if n_elems > 0 else 0
+        ids_a = torch.empty(M, device=dev, dtype=torch.int64)
+        flat_a = torch.empty(M, device=dev, dtype=torch.int32)
+        if M == 0:
+            return tiles, ids_a, flat_a
+        _be.check(lib.rs_isect_emit(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), _be.ptr(cum), C, N,
+                                    tile_width, tile_height, _be.ptr(ids_a), _be.ptr(flat_a), st), "rs_isect_emit")
+        if not sort:
+            return tiles, ids_a, flat_a
+        tile_bits = lib.rs_tile_bits(tile_width, tile_height)
+        cam_bits = int(math.floor(math.log2(C))) + 1
+        end_bit = 32 + tile_bits + cam_bits
+        ids_b = torch.empty_like(ids_a)
+        flat_b = torch.empty_like(flat_a)
+        sb = lib.rs_sort_pairs_temp_bytes(M, 0, end_bit)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        where = _be.check(lib.rs_sort_pairs(_be.ptr(ids_a), _be.ptr(flat_a), _be.ptr(ids_b), _be.ptr(flat_b), M, 0,
+                                            end_bit, _be.ptr(stemp), sb, st), "rs_sort_pairs")
+    return (tiles, ids_b, flat_b) if where == 0 else (tiles, ids_a, flat_a)
+
+
+@torch.no_grad()
+def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
+    """Same call as gsplat ``isect_offset_encode``: -> offsets [C, tile_height, tile_width] i32."""
+    lib = _be.load()
+    _need_cuda(isect_ids)
+    dev = isect_ids.device
+    offsets = torch.empty(n_cameras, tile_height, tile_width, device=dev, dtype=torch.int32)
+    ids = _c(isect_ids, torch.int64)
+    with torch.cuda.device(dev):
+        _be.check(lib.rs_offset_encode(_be.ptr(ids) if ids.numel() else None, ids.numel(), n_cameras, tile_width,
+                                       tile_height, _be.ptr(offsets), _be.stream_ptr(dev)), "rs_offset_encode")
+    return offsets
+
+
+# ------------------------------------------------------------------------------------------------ compositing
+class _RasterizeToPixels(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, ray_ts, ray_planes, normals, backgrounds, Ks, width,
+                height, isect_offsets, flatten_ids, absgrad):
+        lib = _be.load()
+        C, N = opacities.shape
+        dev = means2d.device
+        D = colors.shape[-1]
+        DP = lib.rs_raster_padded_channels(D)
+        if DP < 0:
+            raise NotImplementedError(f"{D} colour channels in one pass (max 72): use channel chunks")
+        color_per_cam = colors.dim() == 3
+        rows = C * N if color_per_cam else N
+        tile_h, tile_w = isect_offsets.shape[1:]
+        M = flatten_ids.numel()
+        f32 = dict(device=dev, dtype=torch.float32)
+        geom = torch.empty(C * N, 16, **f32)
+        out_colors = torch.empty(C, height, width, D, **f32)
+        out_alphas = torch.empty(C, height, width, 1, **f32)
+        out_dexp = torch.empty(C, height, width, 1, **f32)
+        out_dmed = torch.empty(C, height, width, 1, **f32)
+        out_normals = torch.empty(C, height, width, 3, **f32)
+        out_T = torch.empty(C, height, width, **f32)
+        last_ids = torch.empty(C, height, width, device=dev, dtype=torch.int32)
+        median_ids = torch.empty(C, height, width, device=dev, dtype=torch.int32)
+        with torch.cuda.device(dev):
+            st = _be.stream_ptr(dev)
+            _be.check(lib.rs_pack_geom(_be.ptr(means2d), _be.ptr(conics), _be.ptr(opacities), _be.ptr(ray_ts),
+                                       _be.ptr(ray_planes), _be.ptr(normals), None, C * N, _be.ptr(geom), st),
+                      "rs_pack_geom")
+            if DP == D:
+                colors_p = colors
+            else:
+                colors_p = torch.empty(rows, DP, **f32)
+                _be.check(lib.rs_pack_colors(_be.ptr(colors), rows, D, DP, _be.ptr(colors_p), st), "rs_pack_colors")
+            _be.check(lib.rs_rasterize_fwd(
+                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, _be.ptr(backgrounds), _be.ptr(Ks), C, N,
+                width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
+                _be.ptr(out_colors), _be.ptr(out_alphas), _be.ptr(out_dexp), _be.ptr(out_dmed), _be.ptr(out_normals),
+                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), st), "rs_rasterize_fwd")
+        ctx.save_for_backward(geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids,
+                              median_ids)
+        ctx.cfg = (C, N, D, DP, color_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, colors.shape)
+        ctx.means2d_ref = means2d if absgrad else None
+        ctx.mark_non_differentiable(last_ids, median_ids)
+        return out_colors, out_alphas, out_dexp, out_dmed, out_normals, last_ids, median_ids
+
+    @staticmethod
+    def backward(ctx, v_colors, v_alphas, v_dexp, v_dmed, v_normals, _v_last, _v_med):
+        lib = _be.load()
+        geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids, median_ids = ctx.saved_tensors
+        C, N, D, DP, color_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, colors_shape = ctx.cfg
+        dev = geom.device
+        f32 = dict(device=dev, dtype=torch.float32)
+
+        def z(g, shape):
+            return torch.zeros(shape, **f32) if g is None else _c(g)
+
+        v_colors = z(v_colors, (C, height, width, D))
+        v_alphas = z(v_alphas, (C, height, width, 1))
+        v_dexp = z(v_dexp, (C, height, width, 1))
+        v_dmed = z(v_dmed, (C, height, width, 1))
+        v_normals = z(v_normals, (C, height, width, 3))
+        geom_grad = torch.zeros(C * N, 16, **f32)
+        color_grad = torch.zeros(rows, DP, **f32)
+        v_means2d = torch.empty(C, N, 2, **f32)
+        v_abs = torch.empty(C, N, 2, **f32) if absgrad else None
+        v_conics = torch.empty(C, N, 3, **f32)
+        v_opac = torch.empty(C, N, **f32)
+        v_ray_ts = torch.empty(C, N, **f32)
+        v_ray_planes = torch.empty(C, N, 2, **f32)
+        v_nrm = torch.empty(C, N, 3, **f32)
+        with torch.cuda.device(dev):
+            st = _be.stream_ptr(dev)
+            _be.check(lib.rs_rasterize_bwd(
+                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, _be.ptr(backgrounds), _be.ptr(Ks), C, N,
+                width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
+                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), _be.ptr(v_colors), _be.ptr(v_alphas),
+                _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad), _be.ptr(color_grad), st),
+                "rs_rasterize_bwd")
+            _be.check(lib.rs_unpack_geom_grad(_be.ptr(geom_grad), C * N, _be.ptr(v_means2d), _be.ptr(v_abs),
+                                              _be.ptr(v_conics), _be.ptr(v_opac), _be.ptr(v_ray_ts),
+                                              _be.ptr(v_ray_planes), _be.ptr(v_nrm), st), "rs_unpack_geom_grad")
+            if DP == D:
+                v_col = color_grad.view(colors_shape)
+            else:
+                v_col = torch.empty(colors_shape, **f32)
+                _be.check(lib.rs_unpack_colors_grad(_be.ptr(color_grad), rows, D, DP, _be.ptr(v_col), st),
+                          "rs_unpack_colors_grad")
+        if absgrad and ctx.means2d_ref is not None:
+            ctx.means2d_ref.absgrad = v_abs
+        v_bg = None
+        if backgrounds is not None and ctx.needs_input_grad[7]:
+            v_bg = (v_colors * out_T[..., None]).sum(dim=(1, 2))
+        return (v_means2d, v_conics, v_col, v_opac, v_ray_ts, v_ray_planes, v_nrm, v_bg, None, None, None, None,
+                None, None)
+
+
+def rasterize_to_pixels(
+    means2d: Tensor,            # [C,N,2]
+    conics: Tensor,             # [C,N,3]
+    colors: Tensor,             # [C,N,D] or [N,D] (shared by all cameras)
+    opacities: Tensor,          # [C,N]
+    image_width: int,
+    image_height: int,
+    tile_size: int,
+    isect_offsets: Tensor,      # [C,tile_h,tile_w] i32
+    flatten_ids: Tensor,        # [M] i32
+    backgrounds: Optional[Tensor] = None,   # [C,D]
+    masks: Optional[Tensor] = None,
+    packed: bool = False,
+    absgrad: bool = False,
+    ray_ts: Optional[Tensor] = None,        # [C,N]     RaDe: ray distance of the centre
+    ray_planes: Optional[Tensor] = None,    # [C,N,2]   RaDe: -d(ray distance)/d(pixel)
+    normals: Optional[Tensor] = None,       # [C,N,3]   RaDe: camera-space normals
+    Ks: Optional[Tensor] = None,            # [C,3,3]   needed to turn ray distance into z depth
+    return_ids: bool = False,
+):
+    """gsplat ``rasterize_to_pixels`` + the RaDe outputs.  Returns ``(colors [C,H,W,D], alphas [C,H,W,1])``
+    or, when the RaDe inputs are given, ``(colors, alphas, expected_depths [C,H,W,1], median_depths
+    [C,H,W,1], normals [C,H,W,3])``."""
+    if packed or masks is not None:
+        raise NotImplementedError("packed=True / tile masks are not on the collab-splats path")
+    if tile_size != TILE_SIZE:
+        raise NotImplementedError("tile_size must be 16")
+    C, N = opacities.shape
+    assert means2d.shape == (C, N, 2) and conics.shape == (C, N, 3), (means2d.shape, conics.shape)
+    assert colors.shape[:-1] in ((C, N), (N,)), colors.shape
+    rade = ray_ts is not None
+    dev = means2d.device
+    if rade:
+        assert ray_planes is not None and normals is not None and Ks is not None
+    else:
+        ray_ts = torch.zeros(C, N, device=dev)
+        ray_planes = torch.zeros(C, N, 2, device=dev)
+        normals = torch.zeros(C, N, 3, device=dev)
+        Ks = torch.eye(3, device=dev)[None].repeat(C, 1, 1)
+    if backgrounds is not None:
+        assert backgrounds.shape == (C, colors.shape[-1]), backgrounds.shape
+    _need_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
+    out = _RasterizeToPixels.apply(_c(means2d) if not absgrad else means2d, _c(conics), _c(colors), _c(opacities),
+                                   _c(ray_ts), _c(ray_planes), _c(normals), _c(backgrounds), _c(Ks),
+                                   int(image_width), int(image_height), _c(isect_offsets, torch.int32),
+                                   _c(flatten_ids, torch.int32), bool(absgrad))
+    cols, alphas, dexp, dmed, nrm, last_ids, median_ids = out
+    res = (cols, alphas, dexp, dmed, nrm) if rade else (cols, alphas)
+    if return_ids:
+        res = res + (last_ids, median_ids)
+    return res

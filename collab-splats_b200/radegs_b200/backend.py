@@ -1,0 +1,96 @@
+"""ctypes binding of librade_b200.so (include/rade_b200.h).
+
+This is the *only* compute backend: there is no CPU path and no fallback.  If the library has not
+been built (``python __graft_entry__.py build``) loading fails loudly, and every call that returns a
+non-zero status raises ``RuntimeError`` with the library's own message.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / "lib" / "librade_b200.so"
+_lib = None
+
+_p = C.c_void_p
+_i = C.c_int
+_ll = C.c_longlong
+_f = C.c_float
+
+_SIGNATURES = {
+    "rs_version": (C.c_int, []),
+    "rs_error_string": (C.c_char_p, [_i]),
+    "rs_last_cuda_error": (C.c_int, []),
+    "rs_launch_count": (C.c_ulonglong, []),
+    "rs_project_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 8 + [_p]),
+    "rs_project_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_p] * 7 + [_p] * 4 + [_p]),
+    "rs_sh_fwd": (_i, [_i, _i, _ll, _ll, _p, _p, _p, _p, _p]),
+    "rs_sh_bwd": (_i, [_i, _i, _ll, _ll, _p, _p, _p, _p, _p, _p, _p]),
+    "rs_tile_bits": (_i, [_i, _i]),
+    "rs_isect_count": (_i, [_p, _p, _ll, _i, _i, _p, _p]),
+    "rs_cumsum_temp_bytes": (_ll, [_ll]),
+    "rs_cumsum_i32_i64": (_i, [_p, _p, _ll, _p, _ll, _p]),
+    "rs_isect_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "rs_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),
+    "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
+    "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
+    "rs_raster_padded_channels": (_i, [_i]),
+    "rs_pack_geom": (_i, [_p] * 7 + [_ll, _p, _p]),
+    "rs_pack_colors": (_i, [_p, _ll, _i, _i, _p, _p]),
+    "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_p]),
+    "rs_rasterize_bwd": (_i, [_p, _p, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 3 + [_p] * 5 + [_p, _p]
+                         + [_p]),
+    "rs_unpack_geom_grad": (_i, [_p, _ll] + [_p] * 7 + [_p]),
+    "rs_unpack_colors_grad": (_i, [_p, _ll, _i, _i, _p, _p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("rs_set_last_cuda_error", "rs_count_launches")
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises if it is missing -- never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise RuntimeError(
+            f"{_LIB_PATH} not found: the CUDA extension has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU fallback for this path.")
+    lib = C.CDLL(str(_LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> int:
+    if status < 0:
+        lib = load()
+        msg = lib.rs_error_string(status).decode()
+        raise RuntimeError(f"librade_b200 {what} failed: status {status}: {msg}")
+    return status
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be a dense CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("librade_b200 needs CUDA tensors: there is no CPU path")
+    if not t.is_contiguous():
+        raise RuntimeError("librade_b200 needs contiguous tensors")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

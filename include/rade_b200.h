@@ -1,0 +1,121 @@
+/* rade_b200.h -- C ABI of librade_b200.so, the B200 (sm_100a) RaDe-GS rasterizer hot path.
+ *
+ * This is the drop-in boundary for the path collab-splats reaches through gsplat-rade:
+ *   collab_splats/models/rade_gs_model.py:15,20   (imports rasterization, fully_fused_projection)
+ *   collab_splats/models/rade_gs_model.py:373-389 (direct fully_fused_projection call, 8-tuple :392-394)
+ *   collab_splats/models/rade_gs_model.py:439-465 (rasterization(..., return_depth_normal=True))
+ *   collab_splats/models/rade_features_model.py:20,430-434 (spherical_harmonics), :450-476 (rasterization)
+ * gsplat-rade binds its CUDA through a torch C++ extension (gsplat/cuda/_wrapper.py -> csrc/); each entry
+ * point below replaces one of those torch ops with plain pointers and sizes.  The Python mirror of the
+ * gsplat API that calls these (collab-splats_b200/gsplat/) is the reference-side binding; see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to a dense, contiguous array unless it says "host";
+ *   - the caller owns every buffer, including scratch (sizes from the *_temp_bytes functions);
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises, nothing allocates;
+ *   - functions return RS_OK (0) or a negative status; rs_error_string() explains it;
+ *   - C cameras, N Gaussians, images W x H, tiles 16x16 (tile_w = ceil(W/16), tile_h = ceil(H/16)),
+ *     M tile intersections, D blended colour channels.
+ */
+#ifndef RADE_B200_H
+#define RADE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_OK 0
+#define RS_ERR_BAD_ARG (-1)
+#define RS_ERR_LAUNCH (-2)
+#define RS_ERR_UNSUPPORTED (-3)
+
+int rs_version(void);
+const char* rs_error_string(int status);
+int rs_last_cuda_error(void);
+void rs_set_last_cuda_error(int code);
+void rs_count_launches(int n);
+unsigned long long rs_launch_count(void); /* kernels launched through this library so far */
+
+/* ---- projection: replaces gsplat-rade fully_fused_projection fwd (packed=False, pinhole).
+ * means[N,3] quats[N,4] (wxyz, un-normalised) scales[N,3] viewmats[C,4,4] Ks[C,3,3] ->
+ * radii[C,N,2] i32, means2d[C,N,2], depths[C,N], conics[C,N,3], compensations[C,N] (if requested),
+ * ray_ts[C,N], ray_planes[C,N,2], normals[C,N,3]; culled entries are zero-filled. */
+int rs_project_fwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                   const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                   float far_plane, float radius_clip, int calc_compensations, int32_t* radii, float* means2d,
+                   float* depths, float* conics, float* compensations, float* ray_ts, float* ray_planes,
+                   float* normals, void* stream);
+
+/* VJP of the above.  Optional inputs (may be NULL = zero): v_depths, v_compensations, v_ray_ts, v_ray_planes,
+ * v_normals.  Outputs v_means[N,3], v_quats[N,4], v_scales[N,3] are overwritten (summed over cameras);
+ * v_viewmats[C,4,4] is optional (NULL = not wanted). */
+int rs_project_bwd(const float* means, const float* quats, const float* scales, const float* viewmats,
+                   const float* Ks, int C, int N, int width, int height, float eps2d, float near_plane,
+                   float far_plane, float radius_clip, const float* v_means2d, const float* v_depths,
+                   const float* v_conics, const float* v_compensations, const float* v_ray_ts,
+                   const float* v_ray_planes, const float* v_normals, float* v_means, float* v_quats,
+                   float* v_scales, float* v_viewmats, void* stream);
+
+/* ---- spherical harmonics: replaces gsplat spherical_harmonics fwd/bwd (degree <= 3, K <= 16).
+ * dirs[n_elems,3], coeffs[n_coeff_rows,K,3] with row = elem % n_coeff_rows (n_coeff_rows == n_elems, or N when the
+ * coefficients are shared by all cameras), masks[n_elems] u8 or NULL -> colors[n_elems,3]. */
+int rs_sh_fwd(int degree, int K, long long n_elems, long long n_coeff_rows, const float* dirs, const float* coeffs,
+              const uint8_t* masks, float* colors, void* stream);
+int rs_sh_bwd(int degree, int K, long long n_elems, long long n_coeff_rows, const float* dirs, const float* coeffs,
+              const uint8_t* masks, const float* v_colors, float* v_coeffs, float* v_dirs /* NULL ok */,
+              void* stream);
+
+/* ---- tile intersection: replaces gsplat isect_tiles (count pass, scan, emit pass) and isect_offset_encode. */
+int rs_tile_bits(int tile_w, int tile_h); /* bit_length(tile_w*tile_h) */
+int rs_isect_count(const float* means2d, const int32_t* radii, long long n_elems, int tile_w, int tile_h,
+                   int32_t* tiles_per_gauss, void* stream);
+long long rs_cumsum_temp_bytes(long long n);
+int rs_cumsum_i32_i64(const int32_t* in, long long* out_inclusive, long long n, void* temp, long long temp_bytes,
+                      void* stream);
+/* key = cam << (32+tile_bits) | tile << 32 | bits(depth); value = c*N+n; emission order (c, n, tile row, tile col) */
+int rs_isect_emit(const float* means2d, const int32_t* radii, const float* depths, const long long* cum_tiles,
+                  int C, int N, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream);
+int rs_offset_encode(const long long* sorted_isect_ids, long long M, int C, int tile_w, int tile_h,
+                     int32_t* offsets /* [C,tile_h,tile_w] */, void* stream);
+
+/* ---- radix sort: replaces cub::DeviceRadixSort::SortPairs inside isect_tiles(sort=True).
+ * Stable, ascending, on key bits [begin_bit,end_bit).  Clobbers both buffer pairs.
+ * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */
+long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit);
+int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
+                  int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream);
+
+/* ---- compositing: replaces gsplat-rade rasterize_to_pixels fwd/bwd.
+ * Inputs are first packed: geom[C*N,16] (rs_pack_geom) and colours padded to DP = rs_raster_padded_channels(D)
+ * channels (rs_pack_colors; colours may be [C*N,D] (color_per_cam=1) or [N,D] shared by all cameras). */
+int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the host */
+int rs_pack_geom(const float* means2d, const float* conics, const float* opacities /* [C*N] */, const float* ray_ts,
+                 const float* ray_planes, const float* normals, const int32_t* radii /* NULL ok */,
+                 long long n_elems, float* geom, void* stream);
+int rs_pack_colors(const float* colors, long long rows, int D, int DP, float* out, void* stream);
+int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+                     const float* backgrounds /* [C,D] or NULL */, const float* Ks, int C, int N, int width,
+                     int height, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
+                     long long M, float* out_colors /* [C,H,W,D] */, float* out_alphas /* [C,H,W] */,
+                     float* out_expected_depths, float* out_median_depths, float* out_normals /* [C,H,W,3] */,
+                     float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream);
+/* geom_grad[C*N,16] and color_grad[rows,DP] must be zero-filled by the caller; gradients are accumulated. */
+int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+                     const float* backgrounds, const float* Ks, int C, int N, int width, int height, int tile_w,
+                     int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids, long long M,
+                     const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
+                     const float* v_colors, const float* v_alphas, const float* v_expected_depths,
+                     const float* v_median_depths, const float* v_normals, float* geom_grad, float* color_grad,
+                     void* stream);
+int rs_unpack_geom_grad(const float* geom_grad, long long n_elems, float* v_means2d,
+                        float* v_means2d_abs /* NULL ok */, float* v_conics, float* v_opacities, float* v_ray_ts,
+                        float* v_ray_planes, float* v_normals, void* stream);
+int rs_unpack_colors_grad(const float* color_grad, long long rows, int D, int DP, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADE_B200_H */

@@ -458,7 +458,7 @@ def rasterize_to_pixels(
                     row_tiles.append((col.reshape(ph, pw, D), torch.zeros(ph, pw, 1, dtype=dt),
                                       torch.zeros(ph, pw, 1, dtype=dt), torch.zeros(ph, pw, 1, dtype=dt),
                                       torch.zeros(ph, pw, 3, dtype=dt)))
-                    last_ids[c, y0:y1, x0:x1] = s
+                    last_ids[c, y0:y1, x0:x1] = s - 1
                     continue
                 ids = flatten_ids[s:e].long()
                 G = ids.shape[0]
@@ -507,8 +507,7 @@ def rasterize_to_pixels(
                 with torch.no_grad():
                     idxs = torch.arange(G)[None, :].expand(P, G)
                     last = torch.where(contrib, idxs, torch.full_like(idxs, -1)).max(dim=1).values
-                    last_ids[c, y0:y1, x0:x1] = (torch.where(last >= 0, last + s, torch.full_like(last, s))
-                                                 ).to(torch.int32).reshape(ph, pw)
+                    last_ids[c, y0:y1, x0:x1] = (last + s).to(torch.int32).reshape(ph, pw)  # s-1 if none
                     med_ids[c, y0:y1, x0:x1] = torch.where(has_med, mg + s, torch.full_like(mg, -1)
                                                            ).to(torch.int32).reshape(ph, pw)
                     # fragility: decisions within rel 2e-5 of a threshold, among Gaussians actually visited
@@ -600,8 +599,9 @@ def depth_double_to_normal(Ks_c: Tensor, width: int, height: int, depth1: Tensor
     centred principal point: two z-depth maps [H,W] -> normals [2,H,W,3] (border = 0)."""
     dt = depth1.dtype
     fx, fy = Ks_c[0, 0], Ks_c[1, 1]
-    gx = (torch.arange(width, dtype=dt) + 0.5)[None, :].expand(height, width)
-    gy = (torch.arange(height, dtype=dt) + 0.5)[:, None].expand(height, width)
+    dev = depth1.device  # device-agnostic so the tests can apply the same loss to the CUDA outputs
+    gx = (torch.arange(width, dtype=dt, device=dev) + 0.5)[None, :].expand(height, width)
+    gy = (torch.arange(height, dtype=dt, device=dev) + 0.5)[:, None].expand(height, width)
     rx = gx / fx - width / (2 * fx)
     ry = gy / fy - height / (2 * fy)
     rays = torch.stack([rx, ry, torch.ones_like(rx)], dim=0)                # [3,H,W]
