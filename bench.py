@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the RaDe-GS rasterizer hot path (BASELINE.json config 2: rade-gs, 1M Gaussians, one
+1920x1080 view per GPU per step, RGB+ED + expected/median depth + normals, forward + depth-normal loss +
+backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2]
+
+One step = one pass of the hot path over one view per GPU.  Rank 0 prints ONE JSON line (see the contract
+in the task description): `value` is views/s with all inputs resident in HBM, `e2e` is the same metric
+through the public `gsplat.rendering.rasterization` API with the per-step host inputs (camera + ground-truth
+image) copied from pinned host memory and the loss read back, `roofline` describes the dominant kernel,
+`cpu_baseline` is the CPU oracle timed on a bounded sample of the same workload.
+`--impl reference` times the CPU restatement of the reference path (oracle/) on the host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT / "collab-splats_b200"), str(ROOT)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "train views/s, rade-gs fwd+bwd (RGB+ED, expected+median depth, normals, depth-normal loss), " \
+         "1M Gaussians, 1920x1080"
+UNIT = "views/s"
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # NVML missing: report nulls, never fail the bench
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ workload
+class Workload:
+    """rade-gs training step on one view (collab_splats/models/rade_gs_model.py:80-309 restated on device)."""
+
+    def __init__(self, cfg_id: int, device, rank: int, world: int):
+        from radegs_b200 import scenes
+        self.scenes = scenes
+        self.cfg = scenes.BASELINE_CONFIGS[cfg_id]
+        cfg = self.cfg
+        self.device = device
+        gs = scenes.make_gaussians(cfg.n_gaussians, cfg.sh_degree, cfg.n_features, cfg.seed)
+        vm, Ks = scenes.make_cameras(max(world, 1), cfg.width, cfg.height, cfg.seed)
+        self.params = {k: v.to(device).requires_grad_(True) for k, v in gs.items()}
+        self.viewmat_host = vm[rank:rank + 1].contiguous().pin_memory()
+        self.K_host = Ks[rank:rank + 1].contiguous().pin_memory()
+        g = torch.Generator().manual_seed(cfg.seed + 100 + rank)
+        self.gt_host = torch.randint(0, 256, (cfg.height, cfg.width, 3), generator=g, dtype=torch.uint8).pin_memory()
+        self.viewmat = self.viewmat_host.to(device)
+        self.K = self.K_host.to(device)
+        self.gt = self.gt_host.to(device)
+        self.h2d_bytes = self.gt_host.numel() + 4 * (self.viewmat_host.numel() + self.K_host.numel())
+        self.d2h_bytes = 4
+        self.last_meta = None
+
+    def forward_loss(self, viewmat, K, gt_u8):
+        from gsplat.rendering import rasterization
+        from radegs_b200.losses import depth_normal_loss
+        cfg, p = self.cfg, self.params
+        colors = torch.cat([p["features_dc"][:, None, :], p["features_rest"]], dim=1)
+        render, alpha, exp_d, med_d, nrm, meta = rasterization(
+            means=p["means"], quats=p["quats"], scales=torch.exp(p["log_scales"]),
+            opacities=torch.sigmoid(p["opacity_logits"]), colors=colors, viewmats=viewmat, Ks=K, width=cfg.width,
+            height=cfg.height, packed=False, near_plane=0.01, far_plane=1e10, render_mode="RGB+ED",
+            sh_degree=cfg.sh_degree, sparse_grad=False, absgrad=False, rasterize_mode="antialiased",
+            return_depth_normal=True)
+        self.last_meta = meta
+        rgb = torch.clamp(render[0, ..., :3], 0.0, 1.0)
+        l1 = (rgb - gt_u8.float() * (1.0 / 255.0)).abs().mean()
+        dn, _ = depth_normal_loss(K[0], cfg.width, cfg.height, exp_d[0, ..., 0], med_d[0, ..., 0], nrm[0])
+        return l1 + dn
+
+    def zero_grad(self):
+        for v in self.params.values():
+            v.grad = None
+
+    def step_resident(self):
+        self.zero_grad()
+        loss = self.forward_loss(self.viewmat, self.K, self.gt)
+        loss.backward()
+        return loss
+
+    def step_e2e(self):
+        self.zero_grad()
+        vm = self.viewmat_host.to(self.device, non_blocking=True)
+        K = self.K_host.to(self.device, non_blocking=True)
+        gt = self.gt_host.to(self.device, non_blocking=True)
+        loss = self.forward_loss(vm, K, gt)
+        loss.backward()
+        return loss
+
+    def allreduce_grads(self):
+        import torch.distributed as dist
+        flat = torch.cat([v.grad.reshape(-1) for v in self.params.values()])
+        dist.all_reduce(flat)
+        return flat
+
+
+def time_region(fn, steps, world, device):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def stage_times(wl: Workload, reps: int = 5):
+    """Average duration of each stage, timed alone with CUDA events on the launching (current) stream."""
+    from gsplat.cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles, rasterize_to_pixels,
+                                      spherical_harmonics)
+    cfg, p, dev = wl.cfg, wl.params, wl.device
+    out = {}
+
+    def timeit(name, fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name] = e0.elapsed_time(e1) / reps
+        return r
+
+    with torch.no_grad():
+        means, quats = p["means"].detach(), p["quats"].detach()
+        scales, opac = torch.exp(p["log_scales"].detach()), torch.sigmoid(p["opacity_logits"].detach())
+        sh = torch.cat([p["features_dc"].detach()[:, None, :], p["features_rest"].detach()], dim=1)
+        W, H = cfg.width, cfg.height
+        proj = timeit("project_fwd", lambda: fully_fused_projection(means, None, quats, scales, wl.viewmat, wl.K, W, H,
+                                                                     calc_compensations=True))
+        radii, m2, depths, conics, comps, ray_ts, ray_planes, normals = proj
+        dirs = means[None] - torch.linalg.inv_ex(wl.viewmat).inverse[:, :3, 3][:, None]
+        masks = (radii > 0).all(-1)
+        cols = timeit("sh_fwd", lambda: spherical_harmonics(cfg.sh_degree, dirs, sh, masks=masks))
+        cols = torch.cat([torch.clamp_min(cols + 0.5, 0.0), depths[..., None]], dim=-1)
+        tw, th = math.ceil(W / 16), math.ceil(H / 16)
+        tiles, ids, flat = timeit("isect_tiles(count+scan+emit+sort)", lambda: isect_tiles(m2, radii, depths, 16, tw, th))
+        timeit("isect_tiles(unsorted)", lambda: isect_tiles(m2, radii, depths, 16, tw, th, sort=False))
+        out["radix_sort"] = out["isect_tiles(count+scan+emit+sort)"] - out["isect_tiles(unsorted)"]
+        offs = timeit("offset_encode", lambda: isect_offset_encode(ids, 1, tw, th))
+        o = (opac[None] * comps).contiguous()
+        timeit("rasterize_fwd(+pack)", lambda: rasterize_to_pixels(m2, conics, cols, o, W, H, 16, offs, flat, ray_ts=ray_ts,
+                                                                    ray_planes=ray_planes, normals=normals, Ks=wl.K))
+    # backward of the compositing alone
+    leaves = [t.detach().clone().requires_grad_(True) for t in (m2, conics, cols, o, ray_ts, ray_planes, normals)]
+    res = rasterize_to_pixels(leaves[0], leaves[1], leaves[2], leaves[3], W, H, 16, offs, flat, ray_ts=leaves[4],
+                              ray_planes=leaves[5], normals=leaves[6], Ks=wl.K)
+    g = [torch.randn_like(r) for r in res]
+    timeit("rasterize_bwd(+unpack)", lambda: torch.autograd.grad(res, leaves, g, retain_graph=True))
+    M = int(flat.numel())
+    return out, M, 4
+
+
+def cpu_baseline_sample(cfg_id: int, threads: int):
+    """CPU oracle (a restatement of the reference path, kind 'port') on a bounded sample of the workload: all
+    Gaussians projected, a central 256x144 window of the view composited, fwd + loss + bwd."""
+    from oracle import rade_oracle as O
+    from radegs_b200 import scenes
+    from radegs_b200.losses import depth_normal_loss
+    torch.set_num_threads(threads)
+    cfg = scenes.BASELINE_CONFIGS[cfg_id]
+    gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
+    cw, ch = 256, 144
+    x0, y0 = (cfg.width - cw) // 2, (cfg.height - ch) // 2
+    Kc = Ks.clone()
+    Kc[:, 0, 2] -= x0
+    Kc[:, 1, 2] -= y0
+    params = [t.detach().clone().requires_grad_(True) for t in scenes.activate(gs, cfg.sh_degree)]
+    t0 = time.perf_counter()
+    out = O.rasterization(*params, vm, Kc, cw, ch, sh_degree=cfg.sh_degree, render_mode="RGB+ED",
+                          rasterize_mode="antialiased", return_depth_normal=True)
+    rgb = torch.clamp(out[0][0, ..., :3], 0, 1)
+    loss = (rgb - 0.5).abs().mean() + depth_normal_loss(Kc[0], cw, ch, out[2][0, ..., 0], out[3][0, ..., 0], out[4][0])[0]
+    loss.backward()
+    dt = time.perf_counter() - t0
+    frac = (cw * ch) / float(cfg.width * cfg.height)
+    # per-pixel work dominates; scale the window time to the full view (projection is counted once per window,
+    # which favours the CPU number slightly)
+    views_per_s = frac / dt
+    sample = (f"config {cfg_id}: all {cfg.n_gaussians} Gaussians projected, central {cw}x{ch} window "
+              f"({frac * 100:.2f}% of the {cfg.width}x{cfg.height} view) composited fwd+loss+bwd in {dt:.1f} s; "
+              f"value = window fraction / time")
+    return views_per_s, sample, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, sample = [], ""
+    for i in range(args.warmup + args.steps):
+        v, sample, dt = cpu_baseline_sample(args.config, threads)
+        if i >= args.warmup:
+            vals.append(v)
+        if dt * (args.warmup + args.steps - i - 1) > 240:   # keep the whole run within a few minutes
+            if not vals:
+                vals.append(v)
+            break
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE config {args.config} (rade-gs 1M Gaussians, 1 view 1920x1080), CPU oracle",
+                   "note": "gsplat-rade cannot be installed here (SURVEY 8c); this is the CPU restatement (oracle/)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm"
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from radegs_b200 import backend
+    lib = backend.load()
+    warmup = max(args.warmup, 3)
+
+    wl = Workload(args.config, device, rank, world)
+
+    def resident():
+        wl.step_resident()
+        if world > 1:
+            wl.allreduce_grads()
+
+    def e2e():
+        loss = wl.step_e2e()
+        if world > 1:
+            wl.allreduce_grads()
+        return float(loss.item())   # device -> host read of the step's result
+
+    for _ in range(warmup):
+        resident()
+    with ClockSampler(local) as clocks:
+        l0 = lib.rs_launch_count()
+        ms = time_region(resident, args.steps, world, device)
+        launches = int(lib.rs_launch_count() - l0)
+        for _ in range(2):
+            e2e()
+        ms_e2e = time_region(e2e, args.steps, world, device)
+    value = world * args.steps / (ms / 1000.0)
+    value_e2e = world * args.steps / (ms_e2e / 1000.0)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE config {args.config}: rade-gs {wl.cfg.n_gaussians} Gaussians (sh{wl.cfg.sh_degree}), "
+                               f"1 view {wl.cfg.width}x{wl.cfg.height} per GPU per step, RGB+ED antialiased, "
+                               "fwd + L1 + depth-normal loss + bwd",
+                   "views_per_step": world, "parallelism": f"camera-sharded x{world}, Gaussians replicated"
+                                                             + (", NCCL allreduce of parameter grads" if world > 1 else ""),
+                   "l2": "inputs exceed L2 (236 MB of SH coefficients + per-step intersection buffers > 126 MB)",
+                   "optimizer": "none (hot path only)", "n_isects": int(wl.last_meta["flatten_ids"].numel())},
+        "clocks": clocks.summary(),
+        "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+    }
+    if rank == 0:
+        st, M, D = stage_times(wl)
+        peak, how = measured_peaks()
+        P = wl.cfg.width * wl.cfg.height
+        key = "rasterize_bwd(+unpack)"
+        alg_bytes = M * (52 + 4 * D) + P * (4 * D + 36)           # SURVEY 8d, without the atomic-commit term
+        achieved = alg_bytes / (st[key] * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd_kernel<4,256>", "achieved": achieved, "peak": peak,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
+                            "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
+                            "note": "compositing is FP32/issue-bound, not HBM-bound (SURVEY 8d); see DESIGN.md"}
+        line["stage_ms"] = {k: round(v, 4) for k, v in st.items()}
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, sample, _ = cpu_baseline_sample(args.config, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -60,9 +60,10 @@ pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ c
     q0 = make_float4(m.x, m.y, hx, hy);
     q1 = make_float4(0.5f * RS_LOG2E * a, RS_LOG2E * b, 0.5f * RS_LOG2E * c, o);
     float2 rp = __ldg(ray_planes + e);
-    q2 = make_float4(__ldg(ray_ts + e), rp.x, rp.y, 0.f);
+    q2 = make_float4(__ldg(ray_ts + e), rp.x, rp.y, 0.f);  // .w is overwritten with the flatten id below
     q3 = make_float4(__ldg(normals + e * 3), __ldg(normals + e * 3 + 1), __ldg(normals + e * 3 + 2), 0.f);
   }
+  q2.w = __int_as_float((int)e);  // the record carries its own flatten id (bit pattern, never used as a float)
   geom[e * 4 + 0] = q0; geom[e * 4 + 1] = q1; geom[e * 4 + 2] = q2; geom[e * 4 + 3] = q3;
 }
 
@@ -433,7 +434,7 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
           gq[8] = v_t; gq[9] = v_t * dx; gq[10] = v_t * dy;
           gq[12] = vis * v_n0; gq[13] = vis * v_n1; gq[14] = vis * v_n2;
         }
-        const int id = s.ids[buf][jj];  // still batch b's ids: the slot is only recycled after this blend
+        const int id = __float_as_int(q2.w);  // flatten id carried by the record (s.ids is recycled concurrently)
         rs::warp_reduce_scatter<16>(gq, lane);
         {
           const int slot = lane >> 1;

@@ -205,11 +205,14 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
                 ray_planes=ray_planes, normals=normals), offs, flat
 
 
-@pytest.mark.parametrize("D,views,w,h,bg", [(3, 1, 160, 96, False), (4, 2, 100, 70, True), (17, 1, 96, 64, False),
-                                             (67, 1, 64, 48, True), (8, 1, 64, 64, False)])
-def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg):
+@pytest.mark.parametrize("D,views,w,h,bg,n", [(3, 1, 160, 96, False, 2500), (4, 2, 100, 70, True, 2500),
+                                               (17, 1, 96, 64, False, 2500), (67, 1, 64, 48, True, 2500),
+                                               (8, 1, 64, 64, False, 2500),
+                                               # > 256 Gaussians per tile: several staged batches per tile
+                                               (3, 1, 64, 48, False, 9000), (36, 1, 48, 32, False, 4000)])
+def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg, n):
     from gsplat.cuda._wrapper import rasterize_to_pixels
-    cfg, gs, vm, Ks = small_scene(n=2500, w=w, h=h, views=views)
+    cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views)
     inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, D)
     g = torch.Generator().manual_seed(9)
     backgrounds = torch.rand(views, D, generator=g) if bg else None
@@ -235,7 +238,10 @@ def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg):
     assert bool(same_last.all()), f"last_ids differ at {int((~same_last).sum())} robust pixels"
     same_med = (got[6].cpu() == aux["median_ids"]) | aux["fragile"]
     assert bool(same_med.all()), f"median_ids differ at {int((~same_med).sum())} robust pixels"
-    assert float(ref[1].mean()) > 0.3, "scene does not cover the image enough to be a meaningful test"
+    if n > 3000:
+        per_tile = (offs.flatten()[1:] - offs.flatten()[:-1]).max().item()
+        assert per_tile > 600, per_tile
+    assert float(ref[1].mean()) > 0.2, "scene does not cover the image enough to be a meaningful test"
     # backward: random cotangents, zeroed at fragile pixels so both sides differentiate the same branch
     ws = [torch.randn(r.shape, generator=g) * ok_px[..., None] for r in ref[:5]]
     sum((r * x).sum() for r, x in zip(ref[:5], ws)).backward()

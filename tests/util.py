@@ -44,7 +44,14 @@ def close_report(name, got, ref, atol=ATOL, rtol=RTOL, mask=None):
 
 
 def grad_close_report(name, got, ref, rel=2e-3, floor=1e-6):
-    """Gradient check: |got-ref| <= rel*max|ref| + floor (atomics reorder sums, so a global scale)."""
+    """Gradient check: |got-ref| <= rel*max|ref| + floor (atomics reorder sums, so a global scale).
+    A `None` gradient (input not used by the graph) counts as zeros."""
+    if ref is None and got is None:
+        return True, f"{name}: both None"
+    if ref is None:
+        ref = torch.zeros_like(got)
+    if got is None:
+        got = torch.zeros_like(ref)
     got = got.detach().double().cpu()
     ref = ref.detach().double().cpu()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
