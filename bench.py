@@ -299,6 +299,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE resident step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -331,6 +333,14 @@ def main():
 
     for _ in range(warmup):
         resident()
+    if args.profile_step:
+        torch.cuda.synchronize(device)
+        torch.cuda.cudart().cudaProfilerStart()
+        resident()
+        torch.cuda.synchronize(device)
+        torch.cuda.cudart().cudaProfilerStop()
+        print(json.dumps({"profile_step": "done"}))
+        return
     with ClockSampler(local) as clocks:
         l0 = lib.rs_launch_count()
         ms = time_region(resident, args.steps, world, device)

@@ -229,7 +229,8 @@ def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg, n):
                               ray_ts=gpu["ray_ts"], ray_planes=gpu["ray_planes"], normals=gpu["normals"],
                               Ks=Ks.to(cuda_dev), return_ids=True)
     ok_px = ~aux["fragile"]
-    assert int(aux["fragile"].sum()) <= max(4, aux["fragile"].numel() // 500)
+    # near-threshold decisions scale with the number of pairs visited (~1e-5 relative window per decision)
+    assert int(aux["fragile"].sum()) <= max(4, aux["fragile"].numel() // 500, aux["n_tested"] // 100_000)
     names = ["colors", "alphas", "expected_depths", "median_depths", "normals"]
     for i, nm in enumerate(names):
         ok, msg = close_report(nm, got[i], ref[i], mask=ok_px)

@@ -72,7 +72,7 @@ def test_tilted_planar_sheet_depth_and_normal(tilt_deg):
     n_plane = torch.linalg.cross(e1, e2)          # (-sin th, 0, cos th)
     if n_plane[2] > 0:
         n_plane = -n_plane                        # facing the camera (camera looks along +z)
-    gu, gv = torch.meshgrid(torch.linspace(-2.2, 2.2, 90, dtype=dt), torch.linspace(-1.6, 1.6, 66, dtype=dt),
+    gu, gv = torch.meshgrid(torch.linspace(-3.4, 3.4, 140, dtype=dt), torch.linspace(-1.6, 1.6, 66, dtype=dt),
                             indexing="ij")
     means = gu.reshape(-1, 1) * e1 + gv.reshape(-1, 1) * e2
     N = means.shape[0]
