@@ -120,10 +120,12 @@ class Workload:
         self.h2d_bytes = self.gt_host.numel() + 4 * (self.viewmat_host.numel() + self.K_host.numel())
         self.d2h_bytes = 4
         self.last_meta = None
+        self.fused_loss = True
+        self.fx, self.fy = float(Ks[rank, 0, 0]), float(Ks[rank, 1, 1])
 
     def forward_loss(self, viewmat, K, gt_u8):
         from gsplat.rendering import rasterization
-        from radegs_b200.losses import depth_normal_loss
+        from radegs_b200.losses import depth_normal_loss, fused_rade_loss
         cfg, p = self.cfg, self.params
         colors = torch.cat([p["features_dc"][:, None, :], p["features_rest"]], dim=1)
         render, alpha, exp_d, med_d, nrm, meta = rasterization(
@@ -133,6 +135,10 @@ class Workload:
             sh_degree=cfg.sh_degree, sparse_grad=False, absgrad=False, rasterize_mode="antialiased",
             return_depth_normal=True)
         self.last_meta = meta
+        if self.fused_loss:   # csrc/loss.cu: L1 + depth-normal consistency, forward and gradients in one kernel
+            loss, _ = fused_rade_loss(render[0], alpha[0, ..., 0], exp_d[0, ..., 0], med_d[0, ..., 0], nrm[0], gt_u8,
+                                      self.fx, self.fy)
+            return loss
         rgb = torch.clamp(render[0, ..., :3], 0.0, 1.0)
         l1 = (rgb - gt_u8.float() * (1.0 / 255.0)).abs().mean()
         dn, _ = depth_normal_loss(K[0], cfg.width, cfg.height, exp_d[0, ..., 0], med_d[0, ..., 0], nrm[0])
@@ -299,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true", help="use the unfused torch loss glue (for comparison)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE resident step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
@@ -319,6 +326,7 @@ def main():
     warmup = max(args.warmup, 3)
 
     wl = Workload(args.config, device, rank, world)
+    wl.fused_loss = not args.torch_loss
 
     def resident():
         wl.step_resident()

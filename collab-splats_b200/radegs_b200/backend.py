@@ -45,6 +45,7 @@ _SIGNATURES = {
                          + [_p]),
     "rs_unpack_geom_grad": (_i, [_p, _ll] + [_p] * 7 + [_p]),
     "rs_unpack_colors_grad": (_i, [_p, _ll, _i, _i, _p, _p]),
+    "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("rs_set_last_cuda_error", "rs_count_launches")

@@ -40,3 +40,59 @@ def depth_normal_loss(Ks_c: Tensor, width: int, height: int, expected_depth: Ten
     err = 1.0 - (rendered_normals[None] * n_d).sum(dim=-1)
     loss = lam * ((1.0 - depth_ratio) * err[0].mean() + depth_ratio * err[1].mean())
     return loss, err
+
+
+# ------------------------------------------------------------------------------------------------ fused kernel
+class _FusedRadeLoss(torch.autograd.Function):
+    """L1(RGB) + depth-normal consistency for ONE camera in one kernel (csrc/loss.cu): the forward pass also
+    produces the gradients, so backward is a multiply by the upstream scalar (a no-op when it is 1)."""
+
+    @staticmethod
+    def forward(ctx, render, alphas, exp_depth, med_depth, normals, gt_u8, K, background, lam, depth_ratio,
+                use_depth_normal):
+        from . import backend as _be
+        lib = _be.load()
+        H, W, D = render.shape
+        dev = render.device
+        P = H * W
+        sums = torch.zeros(4, device=dev, dtype=torch.float32)
+        v_render = torch.empty_like(render)
+        v_alphas = torch.empty_like(alphas)
+        v_exp = torch.zeros_like(exp_depth)
+        v_med = torch.zeros_like(med_depth)
+        v_nrm = torch.empty_like(normals)
+        w_l1 = 1.0 / (3.0 * P)
+        w_exp = lam * (1.0 - depth_ratio) / P if use_depth_normal else 0.0
+        w_med = lam * depth_ratio / P if use_depth_normal else 0.0
+        fx, fy = K
+        with torch.cuda.device(dev):
+            _be.check(lib.rs_rade_loss_fwd_bwd(
+                _be.ptr(render), _be.ptr(alphas), _be.ptr(exp_depth), _be.ptr(med_depth), _be.ptr(normals),
+                _be.ptr(gt_u8), _be.ptr(background), fx, fy, W, H, D, w_l1, w_exp, w_med, int(use_depth_normal),
+                _be.ptr(sums), _be.ptr(v_render), _be.ptr(v_alphas), _be.ptr(v_exp), _be.ptr(v_med), _be.ptr(v_nrm),
+                _be.stream_ptr(dev)), "rs_rade_loss_fwd_bwd")
+        ctx.save_for_backward(v_render, v_alphas, v_exp, v_med, v_nrm)
+        return sums[3], sums                         # loss, (l1, dn_expected, dn_median, loss)
+
+    @staticmethod
+    def backward(ctx, g_loss, g_terms):
+        # the kernel wrote d(loss)/d(input) for an upstream gradient of 1; scale by the real one in one
+        # multi-tensor kernel (no device->host read of its value).  Gradients w.r.t. the individual terms
+        # are not supported: differentiate the total.
+        out = torch._foreach_mul(list(ctx.saved_tensors), g_loss)
+        return (*out, None, None, None, None, None, None)
+
+
+def fused_rade_loss(render: Tensor, alphas: Tensor, expected_depth: Tensor, median_depth: Tensor,
+                    rendered_normals: Tensor, gt_rgb_u8: Tensor, fx: float, fy: float,
+                    background: Tensor = None, lam: float = 0.05, depth_ratio: float = 0.6,
+                    use_depth_normal: bool = True):
+    """One camera: render [H,W,D>=3], alphas / depths [H,W], normals [H,W,3], gt uint8 [H,W,3] ->
+    (loss, terms[4] = (L1, dn_expected, dn_median, loss)).  Same arithmetic as ``(clamp(rgb)-gt).abs().mean() +
+    depth_normal_loss(...)`` above, fused with its own backward.  `fx, fy` are host floats (the principal point
+    is the image centre, rade_gs_model.py:327-334) so no device->host read is needed."""
+    assert render.dim() == 3 and render.shape[-1] >= 3 and gt_rgb_u8.dtype == torch.uint8
+    c = lambda t: t.contiguous()
+    return _FusedRadeLoss.apply(c(render), c(alphas), c(expected_depth), c(median_depth), c(rendered_normals),
+                                c(gt_rgb_u8), (float(fx), float(fy)), None if background is None else c(background),
+                                float(lam), float(depth_ratio), bool(use_depth_normal))

@@ -115,6 +115,19 @@ int rs_unpack_geom_grad(const float* geom_grad, long long n_elems, float* v_mean
                         float* v_ray_planes, float* v_normals, void* stream);
 int rs_unpack_colors_grad(const float* color_grad, long long rows, int D, int DP, float* out, void* stream);
 
+/* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
+ * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and
+ * collab_splats/models/rade_gs_model.py:202-219,292-307 as run by the training step.
+ * `sums`[4], v_exp_depth and v_med_depth must be zero-filled by the caller.
+ * On return sums = (weighted L1, weighted expected-depth term, weighted median-depth term, total loss); the
+ * written gradients are d(loss)/d(input). */
+int rs_rade_loss_fwd_bwd(const float* render /* [H,W,D] */, const float* alphas, const float* exp_depth,
+                         const float* med_depth, const float* normals /* [H,W,3] */,
+                         const unsigned char* gt_rgb_u8 /* [H,W,3] */, const float* background /* [3] or NULL */,
+                         float fx, float fy, int width, int height, int D, float w_l1, float w_exp, float w_med,
+                         int use_depth_normal, float* sums, float* v_render, float* v_alphas, float* v_exp_depth,
+                         float* v_med_depth, float* v_normals, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -441,3 +441,37 @@ def test_full_size_properties(cuda_dev):
     assert float(dm[..., 0][inside].min()) > 1.0 and float(dm[..., 0][inside].max()) < 5.5
     # every flatten id is a visible Gaussian
     assert bool((meta["radii"].reshape(-1, 2)[meta["flatten_ids"].long()] > 0).all())
+
+
+# ------------------------------------------------------------------------------------------------ fused loss (8f row f1)
+@pytest.mark.parametrize("use_dn,with_bg,D", [(True, False, 4), (True, True, 3), (False, False, 3)])
+def test_fused_loss_matches_reference_glue(cuda_dev, use_dn, with_bg, D):
+    """csrc/loss.cu against the reference's own post-render arithmetic (camera_utils.py:176-279,
+    rade_gs_model.py:202-219,292-307) restated in torch (radegs_b200.losses / the oracle)."""
+    from radegs_b200.losses import fused_rade_loss
+    g = torch.Generator().manual_seed(2)
+    H, W = 70, 93
+    fx, fy = 110.0, 95.0
+    K = torch.tensor([[fx, 0, W / 2], [0, fy, H / 2], [0, 0, 1.0]])
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    base = 3.0 + 0.01 * xx + 0.02 * yy + 0.3 * torch.sin(xx / 7.0) * torch.cos(yy / 5.0)
+    leaves = dict(render=torch.rand(H, W, D, generator=g) * 1.4 - 0.2, alpha=torch.rand(H, W, generator=g),
+                  de=base + 0.05 * torch.rand(H, W, generator=g), dm=base + 0.05 * torch.rand(H, W, generator=g),
+                  nrm=torch.nn.functional.normalize(torch.randn(H, W, 3, generator=g), dim=-1) * 0.9)
+    gt = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    bg = torch.rand(3, generator=g) if with_bg else None
+    cpu = {k: v.clone().requires_grad_(True) for k, v in leaves.items()}
+    rgb = cpu["render"][..., :3] + ((1 - cpu["alpha"])[..., None] * bg if with_bg else 0.0)
+    ref = (torch.clamp(rgb, 0, 1) - gt.float() / 255.0).abs().mean()
+    if use_dn:
+        ref = ref + O.depth_normal_loss(K, W, H, cpu["de"], cpu["dm"], cpu["nrm"])[0]
+    (ref * 3.0).backward()
+    gpu = {k: v.clone().to(cuda_dev).requires_grad_(True) for k, v in leaves.items()}
+    loss, terms = fused_rade_loss(gpu["render"], gpu["alpha"], gpu["de"], gpu["dm"], gpu["nrm"], gt.to(cuda_dev), fx, fy,
+                                  background=None if bg is None else bg.to(cuda_dev), use_depth_normal=use_dn)
+    (loss * 3.0).backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    assert abs(float(terms[:3].sum()) - loss.item()) < 1e-6
+    for k in leaves:
+        ok, msg = grad_close_report("v_" + k, gpu[k].grad, cpu[k].grad, rel=1e-3, floor=1e-9)
+        assert ok, msg
