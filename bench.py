@@ -198,14 +198,16 @@ def stage_times(wl: Workload, reps: int = 5):
 
     def timeit(name, fn):
         fn()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+        ts = []
+        for _ in range(reps):           # one event pair per repetition; report the median
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             r = fn()
-        e1.record()
-        torch.cuda.synchronize(dev)
-        out[name] = e0.elapsed_time(e1) / reps
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        out[name] = sorted(ts)[len(ts) // 2]
         return r
 
     with torch.no_grad():

@@ -1,0 +1,200 @@
+// View-dependent colours for the rasterizer in one kernel: camera position from the view matrix, view
+// direction, real SH (degree <= 3), +0.5, clamp at 0, and the optional depth channel of the "RGB+D/ED" render
+// modes, written straight into the 4-channel padded colour rows the compositing kernel gathers.
+// Replaces, inside gsplat `rasterization()` (reference call rade_gs_model.py:439-465 with
+// sh_degree = 0..3), the chain  inverse(viewmats) -> dirs -> spherical_harmonics -> +0.5 -> clamp_min -> cat(depth)
+// and its autograd (8 kernels forward, ~12 backward upstream) with one forward and one backward kernel.
+//
+// HBM-bound: 12*K B of coefficients per Gaussian dominate (192 B at K = 16).  Coefficient rows are staged
+// through shared memory with coalesced 16-byte accesses (row stride padded to an odd word count, so the
+// per-thread row walks are bank-conflict free); the backward sums over cameras in registers (no atomics).
+#include "common.cuh"
+#include "rade_math.cuh"
+
+namespace {
+
+constexpr int CB = 128;  // Gaussians per block
+
+__device__ __forceinline__ void camera_position(const float* __restrict__ vm, float& px, float& py, float& pz) {
+  // campos = -R^-1 t  (= inverse(viewmat)[:3,3]); R^-1 by cofactors so non-rigid view matrices work too
+  const float a = __ldg(vm + 0), b = __ldg(vm + 1), c = __ldg(vm + 2), tx = __ldg(vm + 3);
+  const float d = __ldg(vm + 4), e = __ldg(vm + 5), f = __ldg(vm + 6), ty = __ldg(vm + 7);
+  const float g = __ldg(vm + 8), h = __ldg(vm + 9), i = __ldg(vm + 10), tz = __ldg(vm + 11);
+  const float A = e * i - f * h, B = -(d * i - f * g), Cc = d * h - e * g;
+  const float idet = 1.0f / (a * A + b * B + c * Cc);
+  const float i00 = A * idet, i01 = (c * h - b * i) * idet, i02 = (b * f - c * e) * idet;
+  const float i10 = B * idet, i11 = (a * i - c * g) * idet, i12 = (c * d - a * f) * idet;
+  const float i20 = Cc * idet, i21 = (b * g - a * h) * idet, i22 = (a * e - b * d) * idet;
+  px = -(i00 * tx + i01 * ty + i02 * tz);
+  py = -(i10 * tx + i11 * ty + i12 * tz);
+  pz = -(i20 * tx + i21 * ty + i22 * tz);
+}
+
+// cooperative, coalesced copy of `count` coefficient rows (row = K*3 floats) global <-> shared (stride RS)
+__device__ __forceinline__ void rows_to_smem(float* s, const float* __restrict__ src, int count, int row, int RS,
+                                             int t) {
+  const int total = count * row;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (int i = t; i < total / 4; i += CB) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int f = i * 4 + k; s[(f / row) * RS + (f % row)] = vv[k]; }
+    }
+  } else {
+    for (int f = t; f < total; f += CB) s[(f / row) * RS + (f % row)] = __ldg(src + f);
+  }
+}
+__device__ __forceinline__ void smem_to_rows(const float* s, float* __restrict__ dst, int count, int row, int RS,
+                                             int t) {
+  const int total = count * row;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    for (int i = t; i < total / 4; i += CB) {
+      float vv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int f = i * 4 + k; vv[k] = s[(f / row) * RS + (f % row)]; }
+      reinterpret_cast<float4*>(dst)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  } else {
+    for (int f = t; f < total; f += CB) dst[f] = s[(f / row) * RS + (f % row)];
+  }
+}
+
+__global__ void __launch_bounds__(CB)
+sh_colors_fwd_kernel(int degree, int K, int C, int N, const float* __restrict__ means,
+                     const float* __restrict__ coeffs, const float* __restrict__ viewmats,
+                     const int2* __restrict__ radii, const float* __restrict__ depths, float4* __restrict__ colors4) {
+  extern __shared__ float s_rows[];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * CB;
+  const int count = min(CB, N - n0);
+  const int row = K * 3, RS = row | 1;
+  rows_to_smem(s_rows, coeffs + (size_t)n0 * row, count, row, RS, t);
+  __syncthreads();
+  if (t >= count) return;
+  const int n = n0 + t;
+  const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
+  const float* cf = s_rows + t * RS;
+  const int nb = (degree + 1) * (degree + 1);
+  for (int c = 0; c < C; ++c) {
+    const size_t e = (size_t)c * N + n;
+    float r = 0.f, g = 0.f, b = 0.f;
+    const int2 rad = __ldg(radii + e);
+    if (rad.x > 0 && rad.y > 0) {
+      float cx, cy, cz;
+      camera_position(viewmats + c * 16, cx, cy, cz);
+      const float x = mx - cx, y = my - cy, z = mz - cz;
+      const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+      float basis[16];
+      rs::sh_basis(degree, x * inv, y * inv, z * inv, basis);
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < nb) { r += basis[q] * cf[q * 3]; g += basis[q] * cf[q * 3 + 1]; b += basis[q] * cf[q * 3 + 2]; }
+    }
+    colors4[e] = make_float4(fmaxf(r + 0.5f, 0.f), fmaxf(g + 0.5f, 0.f), fmaxf(b + 0.5f, 0.f),
+                             depths ? __ldg(depths + e) : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(CB)
+sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ means,
+                     const float* __restrict__ coeffs, const float* __restrict__ viewmats,
+                     const int2* __restrict__ radii, const float4* __restrict__ v_colors4, int has_depth,
+                     float* __restrict__ v_coeffs, float* __restrict__ v_means, float* __restrict__ v_depths) {
+  extern __shared__ float s_rows[];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * CB;
+  const int count = min(CB, N - n0);
+  const int row = K * 3, RS = row | 1;
+  rows_to_smem(s_rows, coeffs + (size_t)n0 * row, count, row, RS, t);
+  __syncthreads();
+  const int nb = (degree + 1) * (degree + 1);
+  float acc[48];
+#pragma unroll
+  for (int i = 0; i < 48; ++i) acc[i] = 0.f;
+  float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+  const int n = n0 + t;
+  if (t < count) {
+    const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
+    const float* cf = s_rows + t * RS;
+    for (int c = 0; c < C; ++c) {
+      const size_t e = (size_t)c * N + n;
+      const float4 vc = __ldg(v_colors4 + e);
+      if (has_depth) v_depths[e] = vc.w;
+      const int2 rad = __ldg(radii + e);
+      if (!(rad.x > 0 && rad.y > 0)) continue;
+      float cx, cy, cz;
+      camera_position(viewmats + c * 16, cx, cy, cz);
+      const float x = mx - cx, y = my - cy, z = mz - cz;
+      const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+      const float ux = x * inv, uy = y * inv, uz = z * inv;
+      float basis[16], gq[16];
+      rs::sh_basis(degree, ux, uy, uz, basis);
+      float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < nb) { r += basis[q] * cf[q * 3]; g += basis[q] * cf[q * 3 + 1]; b += basis[q] * cf[q * 3 + 2]; }
+      // clamp_min(sh + 0.5, 0): gradient passes where the un-clamped value is >= 0
+      const float vr = (r + 0.5f >= 0.f) ? vc.x : 0.f, vg = (g + 0.5f >= 0.f) ? vc.y : 0.f,
+                  vb = (b + 0.5f >= 0.f) ? vc.z : 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        gq[q] = 0.f;
+        if (q < nb) {
+          acc[q * 3] += basis[q] * vr; acc[q * 3 + 1] += basis[q] * vg; acc[q * 3 + 2] += basis[q] * vb;
+          gq[q] = vr * cf[q * 3] + vg * cf[q * 3 + 1] + vb * cf[q * 3 + 2];
+        }
+      }
+      float bx, by, bz;
+      rs::sh_basis_vjp(degree, ux, uy, uz, gq, bx, by, bz);
+      const float dd = ux * bx + uy * by + uz * bz;
+      vmx += (bx - ux * dd) * inv; vmy += (by - uy * dd) * inv; vmz += (bz - uz * dd) * inv;
+    }
+    v_means[n * 3] = vmx; v_means[n * 3 + 1] = vmy; v_means[n * 3 + 2] = vmz;
+  }
+  __syncthreads();  // everyone is done reading the coefficients: reuse the staging buffer for their gradients
+  if (t < count) {
+    float* o = s_rows + t * RS;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q < K) {
+        o[q * 3] = q < nb ? acc[q * 3] : 0.f;
+        o[q * 3 + 1] = q < nb ? acc[q * 3 + 1] : 0.f;
+        o[q * 3 + 2] = q < nb ? acc[q * 3 + 2] : 0.f;
+      }
+  }
+  __syncthreads();
+  smem_to_rows(s_rows, v_coeffs + (size_t)n0 * row, count, row, RS, t);
+}
+
+}  // namespace
+
+// colors4[C,N,4] = (max(SH(dir)+0.5, 0) rgb, depth or 0); coeffs[N,K,3] shared by all cameras; entries whose
+// radii are 0 skip the SH sum (their colour is the clamp of 0.5, as upstream's masked call leaves it).
+extern "C" int rs_sh_colors_fwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                                const float* viewmats, const int32_t* radii, const float* depths, float* colors4,
+                                void* stream) {
+  if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || C < 0 || N < 0) return RS_ERR_BAD_ARG;
+  if (C == 0 || N == 0) return RS_OK;
+  if (!means || !coeffs || !viewmats || !radii || !colors4) return RS_ERR_BAD_ARG;
+  const size_t smem = sizeof(float) * CB * ((K * 3) | 1);
+  sh_colors_fwd_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
+      degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, depths, (float4*)colors4);
+  RS_RETURN_LAST_ERROR();
+}
+
+// VJP: v_colors4[C,N,4] -> v_coeffs[N,K,3] and v_means[N,3] (both summed over cameras, overwritten) and, if
+// has_depth, v_depths[C,N] (the 4th channel's gradient).
+extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                                const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,
+                                float* v_coeffs, float* v_means, float* v_depths, void* stream) {
+  if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || C < 0 || N < 0) return RS_ERR_BAD_ARG;
+  if (N == 0) return RS_OK;
+  if (!means || !coeffs || !viewmats || !radii || !v_colors4 || !v_coeffs || !v_means || (has_depth && !v_depths))
+    return RS_ERR_BAD_ARG;
+  const size_t smem = sizeof(float) * CB * ((K * 3) | 1);
+  sh_colors_bwd_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
+      degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, (const float4*)v_colors4, has_depth, v_coeffs,
+      v_means, v_depths);
+  RS_RETURN_LAST_ERROR();
+}

@@ -30,9 +30,10 @@ template <int DP> struct Batch { static constexpr int value = DP <= 8 ? 256 : (D
 // ------------------------------------------------------------------------------------------------ pack
 __global__ void __launch_bounds__(256)
 pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ conics,
-                 const float* __restrict__ opacities, const float* __restrict__ ray_ts,
-                 const float2* __restrict__ ray_planes, const float* __restrict__ normals,
-                 const int2* __restrict__ radii, long long n_elems, float4* __restrict__ geom) {
+                 const float* __restrict__ opacities, int opac_per_cam, const float* __restrict__ compensations,
+                 int N, const float* __restrict__ ray_ts, const float2* __restrict__ ray_planes,
+                 const float* __restrict__ normals, const int2* __restrict__ radii, long long n_elems,
+                 float4* __restrict__ geom) {
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   if (e >= n_elems) return;
   float4 q0 = make_float4(0.f, 0.f, -1e30f, -1e30f), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -42,7 +43,8 @@ pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ c
   if (live) {
     float2 m = __ldg(means2d + e);
     float a = __ldg(conics + e * 3), b = __ldg(conics + e * 3 + 1), c = __ldg(conics + e * 3 + 2);
-    float o = __ldg(opacities + e);
+    float o = __ldg(opacities + (opac_per_cam ? e : e % N));
+    if (compensations) o *= __ldg(compensations + e);  // antialiased mode: opacity * sqrt(det0/det)
     // footprint of alpha >= 1/255: sigma <= tau = ln(255 o); bbox half extents sqrt(2 tau Sigma_ii), padded
     // so that the test can only ever keep more pairs than the exact per-pair test would
     float hx = 1e30f, hy = 1e30f;
@@ -76,21 +78,58 @@ pack_colors_kernel(const float* __restrict__ colors, long long rows, int D, int 
   out[i] = k < D ? __ldg(colors + r * D + k) : 0.f;
 }
 
+// gradient record layout (16 floats per (camera, Gaussian)):
+//   0 gx  1 gy | 2 ga 3 gb 4 gc (raw conic) | 5 go | 6 g_ray_t 7 g_rpx 8 g_rpy | 9 gnx 10 gny 11 gnz |
+//   12..15 colour channels 0..3 (only when the colours are padded to 4 channels, i.e. DP == 4)
+// thread per Gaussian, looping over cameras, so the opacity gradient (shared by all cameras when the input
+// opacity is [N]) is summed in a register.
 __global__ void __launch_bounds__(256)
-unpack_geom_grad_kernel(const float4* __restrict__ gg, long long n_elems, float2* __restrict__ v_means2d,
+unpack_geom_grad_kernel(const float4* __restrict__ gg, const float2* __restrict__ abs_grad, int C, int N,
+                        const float* __restrict__ opacities, int opac_per_cam,
+                        const float* __restrict__ compensations, float2* __restrict__ v_means2d,
                         float2* __restrict__ v_means2d_abs, float* __restrict__ v_conics,
-                        float* __restrict__ v_opacities, float* __restrict__ v_ray_ts,
-                        float2* __restrict__ v_ray_planes, float* __restrict__ v_normals) {
-  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (e >= n_elems) return;
-  float4 g0 = gg[e * 4], g1 = gg[e * 4 + 1], g2 = gg[e * 4 + 2], g3 = gg[e * 4 + 3];
-  v_means2d[e] = make_float2(g0.x, g0.y);
-  if (v_means2d_abs) v_means2d_abs[e] = make_float2(g0.z, g0.w);
-  v_conics[e * 3] = g1.x; v_conics[e * 3 + 1] = g1.y; v_conics[e * 3 + 2] = g1.z;
-  v_opacities[e] = g1.w;
-  v_ray_ts[e] = g2.x;
-  v_ray_planes[e] = make_float2(g2.y, g2.z);
-  v_normals[e * 3] = g3.x; v_normals[e * 3 + 1] = g3.y; v_normals[e * 3 + 2] = g3.z;
+                        float* __restrict__ v_opacities, float* __restrict__ v_compensations,
+                        float* __restrict__ v_ray_ts, float2* __restrict__ v_ray_planes,
+                        float* __restrict__ v_normals, float* __restrict__ v_colors4, int color_per_cam, int D) {
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  if (n >= N) return;
+  float vo_sum = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const long long e = (long long)c * N + n;
+    const float4 g0 = gg[e * 4], g1 = gg[e * 4 + 1], g2 = gg[e * 4 + 2], g3 = gg[e * 4 + 3];
+    v_means2d[e] = make_float2(g0.x, g0.y);
+    if (v_means2d_abs) v_means2d_abs[e] = abs_grad[e];
+    v_conics[e * 3] = g0.z; v_conics[e * 3 + 1] = g0.w; v_conics[e * 3 + 2] = g1.x;
+    float go = g1.y;
+    if (compensations) {
+      const float comp = __ldg(compensations + e);
+      v_compensations[e] = go * __ldg(opacities + (opac_per_cam ? e : n));
+      go *= comp;
+    }
+    if (opac_per_cam) v_opacities[e] = go; else vo_sum += go;
+    v_ray_ts[e] = g1.z;
+    v_ray_planes[e] = make_float2(g1.w, g2.x);
+    v_normals[e * 3] = g2.y; v_normals[e * 3 + 1] = g2.z; v_normals[e * 3 + 2] = g2.w;
+    if (v_colors4) {
+      if (color_per_cam) {
+        float* o = v_colors4 + e * D;
+        if (D > 0) o[0] = g3.x;
+        if (D > 1) o[1] = g3.y;
+        if (D > 2) o[2] = g3.z;
+        if (D > 3) o[3] = g3.w;
+      } else {
+        c0 += g3.x; c1 += g3.y; c2 += g3.z; c3 += g3.w;
+      }
+    }
+  }
+  if (!opac_per_cam) v_opacities[n] = vo_sum;
+  if (v_colors4 && !color_per_cam) {
+    float* o = v_colors4 + (long long)n * D;
+    if (D > 0) o[0] = c0;
+    if (D > 1) o[1] = c1;
+    if (D > 2) o[2] = c2;
+    if (D > 3) o[3] = c3;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -109,6 +148,7 @@ struct RasterArgs {
   const float* backgrounds;  // [C][D] or null
   const float* Ks;           // [C][9]
   int C, N, W, H, tile_w, tile_h, D, color_per_cam;
+  int ed_channel;            // >= 0: that colour channel is divided by max(alpha, 1e-10) ("ED" modes); -1: none
   const int* offsets;        // [C*tile_h*tile_w]
   const int* flatten_ids;    // [M]
   int M;
@@ -123,8 +163,9 @@ struct RasterArgs {
   int* median_ids;     // [C,H,W]
   // backward inputs / outputs
   const float* v_colors; const float* v_alphas; const float* v_dexp; const float* v_dmed; const float* v_normals;
-  float* geom_grad;    // [C*N][16]
-  float* color_grad;   // [color_rows][DP]
+  float* geom_grad;    // [C*N][16]  (layout: see unpack_geom_grad_kernel)
+  float* color_grad;   // [color_rows][DP]  (DP > 4 only; DP == 4 colours travel in the geometry record)
+  float* abs_grad;     // [C*N][2] or null
 };
 
 template <int DP, int BATCH> struct Smem {
@@ -197,12 +238,13 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
   const int start = c.start, end = c.end;
   const float px = c.px, py = c.py;
 
-  float T = 1.f, dsum = 0.f, tmed = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  // T is the live transmittance and drops to exactly 0 once the pixel has terminated (T_out keeps the value
+  // it had), so "done" needs no flag: a dead pixel fails the T*(1-alpha) > T_STOP test by itself.
+  float T = c.inside ? 1.f : 0.f, T_out = 1.f, dsum = 0.f, tmed = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
   float acc[DP];
 #pragma unroll
   for (int k = 0; k < DP; ++k) acc[k] = 0.f;
   int last_id = start - 1, med_id = -1;
-  bool done = !c.inside;
 
   const int nb = (end - start + BATCH - 1) / BATCH;
   if (nb > 0) {
@@ -211,11 +253,11 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
     issue_gather<DP, BATCH>(s, 0, min(BATCH, end - start), a, t);
     if (nb > 1 && t < BATCH) { const int i = start + BATCH + t; s.ids[1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
   }
-  bool warp_done = __all_sync(RS_FULL_MASK, done);
+  bool warp_done = !__any_sync(RS_FULL_MASK, T != 0.f);
   for (int b = 0; b < nb; ++b) {
     rs::cp_async_wait_all();
     // barrier: batch b has landed, ids[(b+1)&1] are visible, every warp has finished batch b-1
-    if (__syncthreads_count(!done) == 0) break;
+    if (__syncthreads_count(T != 0.f) == 0) break;
     int next_id = 0;
     if (b + 1 < nb) {
       issue_gather<DP, BATCH>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
@@ -243,10 +285,10 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
           const float dx = q0.x - px, dy = q0.y - py;
           const float sig = q1.x * dx * dx + q1.z * dy * dy + q1.y * dx * dy;
           const float alpha = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
-          if (!done && sig >= 0.f && alpha >= RS_ALPHA_MIN) {
+          if (sig >= 0.f && alpha >= RS_ALPHA_MIN) {
             const float nT = T * (1.f - alpha);
-            if (nT <= RS_T_STOP) {
-              done = true;
+            if (!(nT > RS_T_STOP)) {
+              if (T != 0.f) { T_out = T; T = 0.f; }  // terminate: this Gaussian is not blended
             } else {
               const float vis = alpha * T;
               const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
@@ -269,9 +311,8 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
               T = nT;
             }
           }
-          if (__all_sync(RS_FULL_MASK, done)) { warp_done = true; break; }
         }
-        if (warp_done) break;
+        if (!__any_sync(RS_FULL_MASK, T != 0.f)) { warp_done = true; break; }  // all 32 pixels saturated
       }
     }
     if (b + 2 < nb && t < BATCH) s.ids[b & 1][t] = next_id;  // batch b's ids are dead (gather issued last iteration)
@@ -279,13 +320,19 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
   rs::cp_async_wait_all();
 
   if (c.inside) {
+    if (T == 0.f) T = T_out;  // terminated pixel: transmittance in front of the Gaussian that stopped it
     const size_t pix = ((size_t)c.cam * a.H + c.pyi) * a.W + c.pxi;
     const float il = inv_ray_len(a, c.cam, px, py);
     float* oc = a.out_colors + pix * a.D;
     const float* bg = a.backgrounds ? a.backgrounds + (size_t)c.cam * a.D : nullptr;
+    const float ed_scale = 1.f / fmaxf(1.f - T, 1e-10f);
 #pragma unroll
     for (int k = 0; k < DP; ++k)
-      if (k < a.D) oc[k] = acc[k] + (bg ? T * __ldg(bg + k) : 0.f);
+      if (k < a.D) {
+        float v = acc[k] + (bg ? T * __ldg(bg + k) : 0.f);
+        if (k == a.ed_channel) v *= ed_scale;  // expected depth: accumulated depth / alpha
+        oc[k] = v;
+      }
     a.out_alphas[pix] = 1.f - T;
     a.out_T[pix] = T;
 #if RS_NORMALIZE_EXPECTED_DEPTH
@@ -319,7 +366,7 @@ __device__ __forceinline__ void commit_color_grads(const float (&v_c)[DP], float
   }
 }
 
-template <int DP, int BATCH>
+template <int DP, int BATCH, bool ABSGRAD>
 __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
@@ -334,6 +381,18 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
 #pragma unroll
   for (int k = 0; k < DP; ++k) v_c[k] = (inside && k < a.D) ? __ldg(a.v_colors + pix * a.D + k) : 0.f;
   const float T_final = inside ? a.out_T[pix] : 1.f;
+  // "ED" channel: out = S / max(alpha, 1e-10)  ->  v_S = v_out / max(alpha,..),  v_alpha += -out * v_out / alpha
+  float v_alpha_ed = 0.f;
+  if (a.ed_channel >= 0 && inside) {
+    const float alpha_out = 1.f - T_final;
+    const float sc = 1.f / fmaxf(alpha_out, 1e-10f);
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+      if (k == a.ed_channel) {
+        if (alpha_out > 1e-10f) v_alpha_ed = -__ldg(a.out_colors + pix * a.D + k) * v_c[k] * sc;
+        v_c[k] *= sc;
+      }
+  }
   const int last_id = inside ? a.last_ids[pix] : start - 1;
   const int med_id = inside ? a.median_ids[pix] : -1;
   const float il = inside ? inv_ray_len(a, c.cam, px, py) : 0.f;
@@ -351,7 +410,7 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
     for (int k = 0; k < DP; ++k)
       if (k < a.D) bgdot += __ldg(a.backgrounds + (size_t)c.cam * a.D + k) * v_c[k];
   }
-  const float tfin_term = inside ? T_final * (__ldg(a.v_alphas + pix) - bgdot) : 0.f;
+  const float tfin_term = inside ? T_final * (__ldg(a.v_alphas + pix) + v_alpha_ed - bgdot) : 0.f;
   float T = T_final, R = 0.f;
 
   // warp / CTA extent of the lists
@@ -408,9 +467,9 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         float gq[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) gq[k] = 0.f;
-        float vis = 0.f;
+        float vis = 0.f, ax = 0.f, ay = 0.f;
         if (valid) {
-          const float ra = __frcp_rn(1.f - alpha);
+          const float ra = rs::fast_rcp(1.f - alpha);
           T *= ra;  // transmittance in front of this Gaussian
           vis = alpha * T;
           const float tt = q2.x + q2.y * dx + q2.z * dy;
@@ -427,21 +486,34 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
           float v_sig = 0.f, v_o = 0.f;
           if (oe <= RS_ALPHA_MAX) { v_sig = -alpha * v_alpha; v_o = ex * v_alpha; }
           // d sigma / d(dx,dy) with the raw conic (a,b,c) = ln2 * (2 q1.x, q1.y, 2 q1.z)
-          const float gx = v_sig * RS_LN2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
-          const float gy = v_sig * RS_LN2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
-          gq[0] = gx; gq[1] = gy; gq[2] = fabsf(gx); gq[3] = fabsf(gy);
-          gq[4] = 0.5f * dx * dx * v_sig; gq[5] = dx * dy * v_sig; gq[6] = 0.5f * dy * dy * v_sig; gq[7] = v_o;
-          gq[8] = v_t; gq[9] = v_t * dx; gq[10] = v_t * dy;
-          gq[12] = vis * v_n0; gq[13] = vis * v_n1; gq[14] = vis * v_n2;
+          const float vs2 = v_sig * RS_LN2;
+          const float gx = vs2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
+          const float gy = vs2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
+          const float hx = 0.5f * dx * v_sig, hy = 0.5f * dy * v_sig;
+          gq[0] = gx; gq[1] = gy;
+          gq[2] = hx * dx; gq[3] = 2.f * hx * dy; gq[4] = hy * dy; gq[5] = v_o;
+          gq[6] = v_t; gq[7] = v_t * dx; gq[8] = v_t * dy;
+          gq[9] = vis * v_n0; gq[10] = vis * v_n1; gq[11] = vis * v_n2;
+          if constexpr (DP == 4) {
+            gq[12] = vis * v_c[0]; gq[13] = vis * v_c[1]; gq[14] = vis * v_c[2]; gq[15] = vis * v_c[3];
+          }
+          ax = fabsf(gx); ay = fabsf(gy);
         }
         const int id = __float_as_int(q2.w);  // flatten id carried by the record (s.ids is recycled concurrently)
         rs::warp_reduce_scatter<16>(gq, lane);
         {
           const int slot = lane >> 1;
-          if ((lane & 1) == 0 && slot != 11 && slot != 15) atomicAdd(a.geom_grad + (size_t)id * 16 + slot, gq[0]);
+          if ((lane & 1) == 0 && (DP == 4 || slot < 12)) atomicAdd(a.geom_grad + (size_t)id * 16 + slot, gq[0]);
         }
-        const int row = a.color_per_cam ? id : id % a.N;
-        commit_color_grads<DP, 0>(v_c, vis, a.color_grad + (size_t)row * DP, a.D, lane);
+        if constexpr (ABSGRAD) {
+          float ab[2] = {ax, ay};
+          rs::warp_reduce_scatter<2>(ab, lane);
+          if ((lane & 15) == 0) atomicAdd(a.abs_grad + (size_t)id * 2 + (lane >> 4), ab[0]);
+        }
+        if constexpr (DP > 4) {
+          const int row = a.color_per_cam ? id : id % a.N;
+          commit_color_grads<DP, 0>(v_c, vis, a.color_grad + (size_t)row * DP, a.D, lane);
+        }
       }
     }
     if (b >= 2 && t < BATCH) s.ids[b & 1][t] = next_id;
@@ -458,13 +530,17 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   rasterize_fwd_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
-template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
+template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
   const size_t smem = sizeof(Smem<DP, B>);
-  cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B, ABSGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
-  rasterize_bwd_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  rasterize_bwd_kernel<DP, B, ABSGRAD><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
+}
+template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
+  return a.abs_grad ? launch_bwd2<DP, true>(a, st) : launch_bwd2<DP, false>(a, st);
 }
 
 #define RS_DP_LIST(X) X(4) X(8) X(16) X(20) X(32) X(36) X(64) X(68) X(72)
@@ -485,15 +561,16 @@ bool check_common(const RasterArgs& a) {
 
 extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 
-extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, const float* ray_ts,
-                            const float* ray_planes, const float* normals, const int32_t* radii, long long n_elems,
-                            float* geom, void* stream) {
-  if (n_elems < 0) return RS_ERR_BAD_ARG;
+extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, int opac_per_cam,
+                            const float* compensations, int C, int N, const float* ray_ts, const float* ray_planes,
+                            const float* normals, const int32_t* radii, float* geom, void* stream) {
+  if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
+  const long long n_elems = (long long)C * N;
   if (n_elems == 0) return RS_OK;
   if (!means2d || !conics || !opacities || !ray_ts || !ray_planes || !normals || !geom) return RS_ERR_BAD_ARG;
   pack_geom_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float2*)means2d, conics, opacities, ray_ts, (const float2*)ray_planes, normals, (const int2*)radii,
-      n_elems, (float4*)geom);
+      (const float2*)means2d, conics, opacities, opac_per_cam, compensations, N, ray_ts, (const float2*)ray_planes,
+      normals, (const int2*)radii, n_elems, (float4*)geom);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -505,16 +582,22 @@ extern "C" int rs_pack_colors(const float* colors, long long rows, int D, int DP
   RS_RETURN_LAST_ERROR();
 }
 
-extern "C" int rs_unpack_geom_grad(const float* geom_grad, long long n_elems, float* v_means2d, float* v_means2d_abs,
-                                   float* v_conics, float* v_opacities, float* v_ray_ts, float* v_ray_planes,
-                                   float* v_normals, void* stream) {
-  if (n_elems < 0) return RS_ERR_BAD_ARG;
-  if (n_elems == 0) return RS_OK;
+extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad, int C, int N,
+                                   const float* opacities, int opac_per_cam, const float* compensations,
+                                   float* v_means2d, float* v_means2d_abs, float* v_conics, float* v_opacities,
+                                   float* v_compensations, float* v_ray_ts, float* v_ray_planes, float* v_normals,
+                                   float* v_colors4, int color_per_cam, int D, void* stream) {
+  if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
+  if ((long long)C * N == 0) return RS_OK;
   if (!geom_grad || !v_means2d || !v_conics || !v_opacities || !v_ray_ts || !v_ray_planes || !v_normals)
     return RS_ERR_BAD_ARG;
-  unpack_geom_grad_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)geom_grad, n_elems, (float2*)v_means2d, (float2*)v_means2d_abs, v_conics, v_opacities, v_ray_ts,
-      (float2*)v_ray_planes, v_normals);
+  if (v_means2d_abs && !abs_grad) return RS_ERR_BAD_ARG;
+  if (compensations && (!opacities || !v_compensations)) return RS_ERR_BAD_ARG;
+  if (v_colors4 && (D < 1 || D > 4)) return RS_ERR_BAD_ARG;
+  unpack_geom_grad_kernel<<<rs_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)geom_grad, (const float2*)abs_grad, C, N, opacities, opac_per_cam, compensations,
+      (float2*)v_means2d, (float2*)v_means2d_abs, v_conics, v_opacities, v_compensations, v_ray_ts,
+      (float2*)v_ray_planes, v_normals, v_colors4, color_per_cam, D);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -527,21 +610,23 @@ extern "C" int rs_unpack_colors_grad(const float* color_grad, long long rows, in
 }
 
 extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
-                                const float* backgrounds, const float* Ks, int C, int N, int width, int height,
-                                int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
-                                long long M, float* out_colors, float* out_alphas, float* out_expected_depths,
-                                float* out_median_depths, float* out_normals, float* out_transmittance,
-                                int32_t* last_ids, int32_t* median_ids, void* stream) {
+                                int ed_channel, const float* backgrounds, const float* Ks, int C, int N, int width,
+                                int height, int tile_w, int tile_h, const int32_t* tile_offsets,
+                                const int32_t* flatten_ids, long long M, float* out_colors, float* out_alphas,
+                                float* out_expected_depths, float* out_median_depths, float* out_normals,
+                                float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream) {
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
   a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
+  a.ed_channel = ed_channel;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
   if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
     return RS_ERR_BAD_ARG;
+  if (ed_channel >= D) return RS_ERR_BAD_ARG;
   if (tile_w != rs_div_up(width, RS_TILE) || tile_h != rs_div_up(height, RS_TILE)) return RS_ERR_BAD_ARG;
   const int DP = padded_channels(D);
   cudaStream_t st = (cudaStream_t)stream;
@@ -554,27 +639,30 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
 }
 
 extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
-                                const float* backgrounds, const float* Ks, int C, int N, int width, int height,
-                                int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
-                                long long M, const float* transmittance, const int32_t* last_ids,
-                                const int32_t* median_ids, const float* v_colors, const float* v_alphas,
-                                const float* v_expected_depths, const float* v_median_depths, const float* v_normals,
-                                float* geom_grad, float* color_grad, void* stream) {
+                                int ed_channel, const float* backgrounds, const float* Ks, int C, int N, int width,
+                                int height, int tile_w, int tile_h, const int32_t* tile_offsets,
+                                const int32_t* flatten_ids, long long M, const float* out_colors,
+                                const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
+                                const float* v_colors, const float* v_alphas, const float* v_expected_depths,
+                                const float* v_median_depths, const float* v_normals, float* geom_grad,
+                                float* color_grad, float* abs_grad, void* stream) {
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
   a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
+  a.ed_channel = ed_channel;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
+  a.out_colors = (float*)out_colors;
   a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;
   a.v_colors = v_colors; a.v_alphas = v_alphas; a.v_dexp = v_expected_depths; a.v_dmed = v_median_depths;
-  a.v_normals = v_normals; a.geom_grad = geom_grad; a.color_grad = color_grad;
+  a.v_normals = v_normals; a.geom_grad = geom_grad; a.color_grad = color_grad; a.abs_grad = abs_grad;
+  const int DP = padded_channels(D);
   if (!check_common(a) || !v_colors || !v_alphas || !v_expected_depths || !v_median_depths || !v_normals ||
-      !geom_grad || !color_grad)
+      !geom_grad || (DP > 4 && !color_grad) || (ed_channel >= 0 && !out_colors) || ed_channel >= D)
     return RS_ERR_BAD_ARG;
   if (tile_w != rs_div_up(width, RS_TILE) || tile_h != rs_div_up(height, RS_TILE)) return RS_ERR_BAD_ARG;
   if (M == 0) return RS_OK;
-  const int DP = padded_channels(D);
   cudaStream_t st = (cudaStream_t)stream;
   switch (DP) {
 #define X(v) case v: return launch_bwd<v>(a, st);

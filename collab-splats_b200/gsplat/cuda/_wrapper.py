@@ -261,19 +261,66 @@ def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile
     return offsets
 
 
+# ------------------------------------------------------------------------------------------------ SH colours (fused)
+class _SHColors(torch.autograd.Function):
+    """campos -> dirs -> SH -> +0.5 -> clamp_min(0) -> [rgb | depth] in one kernel each way (csrc/colors.cu)."""
+
+    @staticmethod
+    def forward(ctx, degree, means, coeffs, viewmats, radii, depths):
+        lib = _be.load()
+        C, N, K = viewmats.shape[0], means.shape[0], coeffs.shape[-2]
+        colors4 = torch.empty(C, N, 4, device=means.device, dtype=torch.float32)
+        with torch.cuda.device(means.device):
+            _be.check(lib.rs_sh_colors_fwd(degree, K, C, N, _be.ptr(means), _be.ptr(coeffs), _be.ptr(viewmats),
+                                           _be.ptr(radii), _be.ptr(depths), _be.ptr(colors4),
+                                           _be.stream_ptr(means.device)), "rs_sh_colors_fwd")
+        ctx.save_for_backward(means, coeffs, viewmats, radii)
+        ctx.cfg = (degree, depths is not None)
+        return colors4
+
+    @staticmethod
+    def backward(ctx, v_colors4):
+        lib = _be.load()
+        means, coeffs, viewmats, radii = ctx.saved_tensors
+        degree, has_depth = ctx.cfg
+        C, N, K = viewmats.shape[0], means.shape[0], coeffs.shape[-2]
+        v_coeffs = torch.empty_like(coeffs)
+        v_means = torch.empty_like(means)
+        v_depths = torch.empty(C, N, device=means.device, dtype=torch.float32) if has_depth else None
+        with torch.cuda.device(means.device):
+            _be.check(lib.rs_sh_colors_bwd(degree, K, C, N, _be.ptr(means), _be.ptr(coeffs), _be.ptr(viewmats),
+                                           _be.ptr(radii), _be.ptr(_c(v_colors4)), int(has_depth), _be.ptr(v_coeffs),
+                                           _be.ptr(v_means), _be.ptr(v_depths), _be.stream_ptr(means.device)),
+                      "rs_sh_colors_bwd")
+        return None, v_means, v_coeffs, None, None, v_depths
+
+
+def sh_colors(degree: int, means: Tensor, coeffs: Tensor, viewmats: Tensor, radii: Tensor,
+              depths: Optional[Tensor] = None) -> Tensor:
+    """View-dependent colours as `rasterization()` computes them, fused:
+    ``clamp_min(spherical_harmonics(degree, means - campos, coeffs, masks=radii>0) + 0.5, 0)`` with the depth
+    channel of the RGB+D / RGB+ED modes appended -> [C,N,4] (4th channel 0 when `depths` is None).
+    means [N,3], coeffs [N,K,3] (shared by all cameras), viewmats [C,4,4], radii [C,N,2], depths [C,N]."""
+    N, K = means.shape[0], coeffs.shape[-2]
+    assert coeffs.shape == (N, K, 3) and 0 <= degree <= 3 and (degree + 1) ** 2 <= K <= 16, (coeffs.shape, degree)
+    _need_cuda(means, coeffs, viewmats, radii, depths)
+    return _SHColors.apply(int(degree), _c(means), _c(coeffs), _c(viewmats), _c(radii, torch.int32), _c(depths))
+
+
 # ------------------------------------------------------------------------------------------------ compositing
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means2d, conics, colors, opacities, ray_ts, ray_planes, normals, backgrounds, Ks, width,
-                height, isect_offsets, flatten_ids, absgrad):
+    def forward(ctx, means2d, conics, colors, opacities, compensations, ray_ts, ray_planes, normals, backgrounds,
+                Ks, width, height, isect_offsets, flatten_ids, absgrad, ed_channel):
         lib = _be.load()
-        C, N = opacities.shape
+        C, N = means2d.shape[:2]
         dev = means2d.device
         D = colors.shape[-1]
         DP = lib.rs_raster_padded_channels(D)
         if DP < 0:
             raise NotImplementedError(f"{D} colour channels in one pass (max 72): use channel chunks")
         color_per_cam = colors.dim() == 3
+        opac_per_cam = opacities.dim() == 2
         rows = C * N if color_per_cam else N
         tile_h, tile_w = isect_offsets.shape[1:]
         M = flatten_ids.numel()
@@ -289,22 +336,23 @@ class _RasterizeToPixels(torch.autograd.Function):
         median_ids = torch.empty(C, height, width, device=dev, dtype=torch.int32)
         with torch.cuda.device(dev):
             st = _be.stream_ptr(dev)
-            _be.check(lib.rs_pack_geom(_be.ptr(means2d), _be.ptr(conics), _be.ptr(opacities), _be.ptr(ray_ts),
-                                       _be.ptr(ray_planes), _be.ptr(normals), None, C * N, _be.ptr(geom), st),
-                      "rs_pack_geom")
+            _be.check(lib.rs_pack_geom(_be.ptr(means2d), _be.ptr(conics), _be.ptr(opacities), int(opac_per_cam),
+                                       _be.ptr(compensations), C, N, _be.ptr(ray_ts), _be.ptr(ray_planes),
+                                       _be.ptr(normals), None, _be.ptr(geom), st), "rs_pack_geom")
             if DP == D:
                 colors_p = colors
             else:
                 colors_p = torch.empty(rows, DP, **f32)
                 _be.check(lib.rs_pack_colors(_be.ptr(colors), rows, D, DP, _be.ptr(colors_p), st), "rs_pack_colors")
             _be.check(lib.rs_rasterize_fwd(
-                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, _be.ptr(backgrounds), _be.ptr(Ks), C, N,
-                width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
+                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, ed_channel, _be.ptr(backgrounds), _be.ptr(Ks),
+                C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
                 _be.ptr(out_colors), _be.ptr(out_alphas), _be.ptr(out_dexp), _be.ptr(out_dmed), _be.ptr(out_normals),
                 _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), st), "rs_rasterize_fwd")
         ctx.save_for_backward(geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids,
-                              median_ids)
-        ctx.cfg = (C, N, D, DP, color_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, colors.shape)
+                              median_ids, opacities, compensations, out_colors if ed_channel >= 0 else None)
+        ctx.cfg = (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad,
+                   ed_channel, colors.shape)
         ctx.means2d_ref = means2d if absgrad else None
         ctx.mark_non_differentiable(last_ids, median_ids)
         return out_colors, out_alphas, out_dexp, out_dmed, out_normals, last_ids, median_ids
@@ -312,8 +360,10 @@ class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def backward(ctx, v_colors, v_alphas, v_dexp, v_dmed, v_normals, _v_last, _v_med):
         lib = _be.load()
-        geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids, median_ids = ctx.saved_tensors
-        C, N, D, DP, color_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, colors_shape = ctx.cfg
+        (geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids, median_ids, opacities,
+         compensations, out_colors) = ctx.saved_tensors
+        (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, ed_channel,
+         colors_shape) = ctx.cfg
         dev = geom.device
         f32 = dict(device=dev, dtype=torch.float32)
 
@@ -326,45 +376,50 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_dmed = z(v_dmed, (C, height, width, 1))
         v_normals = z(v_normals, (C, height, width, 3))
         geom_grad = torch.zeros(C * N, 16, **f32)
-        color_grad = torch.zeros(rows, DP, **f32)
+        color_grad = torch.zeros(rows, DP, **f32) if DP > 4 else None
+        abs_grad = torch.zeros(C * N, 2, **f32) if absgrad else None
         v_means2d = torch.empty(C, N, 2, **f32)
         v_abs = torch.empty(C, N, 2, **f32) if absgrad else None
         v_conics = torch.empty(C, N, 3, **f32)
-        v_opac = torch.empty(C, N, **f32)
+        v_opac = torch.empty(opacities.shape, **f32)
+        v_comps = torch.empty(C, N, **f32) if compensations is not None else None
         v_ray_ts = torch.empty(C, N, **f32)
         v_ray_planes = torch.empty(C, N, 2, **f32)
         v_nrm = torch.empty(C, N, 3, **f32)
+        v_col = torch.empty(colors_shape, **f32)
         with torch.cuda.device(dev):
             st = _be.stream_ptr(dev)
             _be.check(lib.rs_rasterize_bwd(
-                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, _be.ptr(backgrounds), _be.ptr(Ks), C, N,
-                width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
-                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), _be.ptr(v_colors), _be.ptr(v_alphas),
-                _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad), _be.ptr(color_grad), st),
-                "rs_rasterize_bwd")
-            _be.check(lib.rs_unpack_geom_grad(_be.ptr(geom_grad), C * N, _be.ptr(v_means2d), _be.ptr(v_abs),
-                                              _be.ptr(v_conics), _be.ptr(v_opac), _be.ptr(v_ray_ts),
-                                              _be.ptr(v_ray_planes), _be.ptr(v_nrm), st), "rs_unpack_geom_grad")
-            if DP == D:
-                v_col = color_grad.view(colors_shape)
-            else:
-                v_col = torch.empty(colors_shape, **f32)
-                _be.check(lib.rs_unpack_colors_grad(_be.ptr(color_grad), rows, D, DP, _be.ptr(v_col), st),
-                          "rs_unpack_colors_grad")
+                _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, ed_channel, _be.ptr(backgrounds), _be.ptr(Ks),
+                C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
+                _be.ptr(out_colors), _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), _be.ptr(v_colors),
+                _be.ptr(v_alphas), _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad),
+                _be.ptr(color_grad), _be.ptr(abs_grad), st), "rs_rasterize_bwd")
+            _be.check(lib.rs_unpack_geom_grad(
+                _be.ptr(geom_grad), _be.ptr(abs_grad), C, N, _be.ptr(opacities), int(opac_per_cam),
+                _be.ptr(compensations), _be.ptr(v_means2d), _be.ptr(v_abs), _be.ptr(v_conics), _be.ptr(v_opac),
+                _be.ptr(v_comps), _be.ptr(v_ray_ts), _be.ptr(v_ray_planes), _be.ptr(v_nrm),
+                _be.ptr(v_col) if DP == 4 else None, int(color_per_cam), D, st), "rs_unpack_geom_grad")
+            if DP > 4:
+                if DP == D:
+                    v_col = color_grad.view(colors_shape)
+                else:
+                    _be.check(lib.rs_unpack_colors_grad(_be.ptr(color_grad), rows, D, DP, _be.ptr(v_col), st),
+                              "rs_unpack_colors_grad")
         if absgrad and ctx.means2d_ref is not None:
             ctx.means2d_ref.absgrad = v_abs
         v_bg = None
-        if backgrounds is not None and ctx.needs_input_grad[7]:
+        if backgrounds is not None and ctx.needs_input_grad[8]:
             v_bg = (v_colors * out_T[..., None]).sum(dim=(1, 2))
-        return (v_means2d, v_conics, v_col, v_opac, v_ray_ts, v_ray_planes, v_nrm, v_bg, None, None, None, None,
-                None, None)
+        return (v_means2d, v_conics, v_col, v_opac, v_comps, v_ray_ts, v_ray_planes, v_nrm, v_bg, None, None, None,
+                None, None, None, None)
 
 
 def rasterize_to_pixels(
     means2d: Tensor,            # [C,N,2]
     conics: Tensor,             # [C,N,3]
     colors: Tensor,             # [C,N,D] or [N,D] (shared by all cameras)
-    opacities: Tensor,          # [C,N]
+    opacities: Tensor,          # [C,N], or [N] (shared by all cameras)
     image_width: int,
     image_height: int,
     tile_size: int,
@@ -379,6 +434,8 @@ def rasterize_to_pixels(
     normals: Optional[Tensor] = None,       # [C,N,3]   RaDe: camera-space normals
     Ks: Optional[Tensor] = None,            # [C,3,3]   needed to turn ray distance into z depth
     return_ids: bool = False,
+    compensations: Optional[Tensor] = None,  # [C,N]    fused: effective opacity = opacities * compensations
+    ed_channel: int = -1,                    # fused "ED": that output channel is divided by max(alpha, 1e-10)
 ):
     """gsplat ``rasterize_to_pixels`` + the RaDe outputs.  Returns ``(colors [C,H,W,D], alphas [C,H,W,1])``
     or, when the RaDe inputs are given, ``(colors, alphas, expected_depths [C,H,W,1], median_depths
@@ -387,9 +444,11 @@ def rasterize_to_pixels(
         raise NotImplementedError("packed=True / tile masks are not on the collab-splats path")
     if tile_size != TILE_SIZE:
         raise NotImplementedError("tile_size must be 16")
-    C, N = opacities.shape
+    C, N = means2d.shape[:2]
     assert means2d.shape == (C, N, 2) and conics.shape == (C, N, 3), (means2d.shape, conics.shape)
     assert colors.shape[:-1] in ((C, N), (N,)), colors.shape
+    assert opacities.shape in ((C, N), (N,)), opacities.shape
+    assert compensations is None or compensations.shape == (C, N)
     rade = ray_ts is not None
     dev = means2d.device
     if rade:
@@ -403,9 +462,9 @@ def rasterize_to_pixels(
         assert backgrounds.shape == (C, colors.shape[-1]), backgrounds.shape
     _need_cuda(means2d, conics, colors, opacities, isect_offsets, flatten_ids)
     out = _RasterizeToPixels.apply(_c(means2d) if not absgrad else means2d, _c(conics), _c(colors), _c(opacities),
-                                   _c(ray_ts), _c(ray_planes), _c(normals), _c(backgrounds), _c(Ks),
-                                   int(image_width), int(image_height), _c(isect_offsets, torch.int32),
-                                   _c(flatten_ids, torch.int32), bool(absgrad))
+                                   _c(compensations), _c(ray_ts), _c(ray_planes), _c(normals), _c(backgrounds),
+                                   _c(Ks), int(image_width), int(image_height), _c(isect_offsets, torch.int32),
+                                   _c(flatten_ids, torch.int32), bool(absgrad), int(ed_channel))
     cols, alphas, dexp, dmed, nrm, last_ids, median_ids = out
     res = (cols, alphas, dexp, dmed, nrm) if rade else (cols, alphas)
     if return_ids:

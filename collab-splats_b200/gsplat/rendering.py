@@ -17,7 +17,7 @@ import torch
 from torch import Tensor
 
 from .cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles, rasterize_to_pixels,
-                            spherical_harmonics)
+                            sh_colors, spherical_harmonics)
 
 MAX_CHANNELS_PER_PASS = 72
 
@@ -86,29 +86,38 @@ def rasterization(
         means, None, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
         far_plane=far_plane, radius_clip=radius_clip, packed=False, sparse_grad=False,
         calc_compensations=(rasterize_mode == "antialiased"))
-    opac = opacities[None, :].expand(C, N)
-    if compensations is not None:
-        opac = opac * compensations
+    # effective opacity = opacity * compensation is formed inside the pack kernel (and its VJP in the unpack
+    # kernel); the [C,N] product below only feeds `meta` (detached, never differentiated)
+    with torch.no_grad():
+        opac_meta = opacities[None, :].expand(C, N) if compensations is None else opacities[None, :] * compensations
 
     # ---- colours
-    if sh_degree is None:
-        cols = colors                              # [N,D] is shared by all cameras without expansion
-    else:
-        campos = torch.linalg.inv_ex(viewmats, check_errors=False).inverse[:, :3, 3]
-        dirs = means[None, :, :] - campos[:, None, :]
-        masks = (radii > 0).all(dim=-1)
-        cols = spherical_harmonics(sh_degree, dirs, colors, masks=masks)
-        cols = torch.clamp_min(cols + 0.5, 0.0)
-    if render_mode in ("RGB+D", "RGB+ED"):
-        if cols.dim() == 2:
-            cols = cols[None].expand(C, N, cols.shape[-1])
-        cols = torch.cat([cols, depths[..., None]], dim=-1)
-        if backgrounds is not None:
-            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device)], dim=-1)
-    elif render_mode in ("D", "ED"):
+    with_depth = render_mode in ("RGB+D", "RGB+ED")
+    slice_rgb = False
+    if render_mode in ("D", "ED"):
         cols = depths[..., None]
         if backgrounds is not None:
             backgrounds = torch.zeros(C, 1, device=backgrounds.device)
+    elif sh_degree is not None and colors.dim() == 3:
+        # fused: campos -> dirs -> SH -> +0.5 -> clamp -> [rgb | depth], 4 channels (4th = 0 in plain RGB mode)
+        cols = sh_colors(sh_degree, means, colors, viewmats, radii, depths if with_depth else None)
+        slice_rgb = not with_depth
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device)], dim=-1)
+    else:
+        if sh_degree is None:
+            cols = colors                          # [N,D] is shared by all cameras without expansion
+        else:                                      # per-camera SH coefficients [C,N,K,3]
+            campos = torch.linalg.inv_ex(viewmats, check_errors=False).inverse[:, :3, 3]
+            dirs = means[None, :, :] - campos[:, None, :]
+            cols = spherical_harmonics(sh_degree, dirs, colors, masks=(radii > 0).all(dim=-1))
+            cols = torch.clamp_min(cols + 0.5, 0.0)
+        if with_depth:
+            if cols.dim() == 2:
+                cols = cols[None].expand(C, N, cols.shape[-1])
+            cols = torch.cat([cols, depths[..., None]], dim=-1)
+            if backgrounds is not None:
+                backgrounds = torch.cat([backgrounds, torch.zeros(C, 1, device=backgrounds.device)], dim=-1)
 
     # ---- tile intersection, sort, offsets
     tile_width = math.ceil(width / float(tile_size))
@@ -117,32 +126,36 @@ def rasterization(
                                                           packed=False, n_cameras=C)
     isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height)
 
-    # ---- compositing (one pass up to 72 channels; wider colours are split, geometry comes from the first pass)
+    # ---- compositing (one pass up to 72 channels; wider colours are split, geometry comes from the first pass).
+    # The "ED" normalisation (depth channel / alpha) runs in the kernel epilogue.
     D = cols.shape[-1]
+    ed = render_mode in ("ED", "RGB+ED")
     if D <= MAX_CHANNELS_PER_PASS:
         render_colors, render_alphas, exp_d, med_d, nrm = rasterize_to_pixels(
-            means2d, conics, cols, opac, width, height, tile_size, isect_offsets, flatten_ids,
-            backgrounds=backgrounds, absgrad=absgrad, ray_ts=ray_ts, ray_planes=ray_planes, normals=normals, Ks=Ks)
+            means2d, conics, cols, opacities, width, height, tile_size, isect_offsets, flatten_ids,
+            backgrounds=backgrounds, absgrad=absgrad, ray_ts=ray_ts, ray_planes=ray_planes, normals=normals, Ks=Ks,
+            compensations=compensations, ed_channel=(D - 1) if ed else -1)
     else:
         chunk = 64
         parts = []
         render_alphas = exp_d = med_d = nrm = None
         for k0 in range(0, D, chunk):
-            bg = backgrounds[:, k0:k0 + chunk] if backgrounds is not None else None
-            out = rasterize_to_pixels(means2d, conics, cols[..., k0:k0 + chunk], opac, width, height, tile_size,
+            k1 = min(k0 + chunk, D)
+            bg = backgrounds[:, k0:k1] if backgrounds is not None else None
+            out = rasterize_to_pixels(means2d, conics, cols[..., k0:k1], opacities, width, height, tile_size,
                                       isect_offsets, flatten_ids, backgrounds=bg, absgrad=absgrad, ray_ts=ray_ts,
-                                      ray_planes=ray_planes, normals=normals, Ks=Ks)
+                                      ray_planes=ray_planes, normals=normals, Ks=Ks, compensations=compensations,
+                                      ed_channel=(k1 - k0 - 1) if (ed and k1 == D) else -1)
             parts.append(out[0])
             if k0 == 0:
                 render_alphas, exp_d, med_d, nrm = out[1:]
         render_colors = torch.cat(parts, dim=-1)
-    if render_mode in ("ED", "RGB+ED"):
-        render_colors = torch.cat([render_colors[..., :-1],
-                                   render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1)
+    if slice_rgb:
+        render_colors = render_colors[..., :3]
 
     meta: Dict = {
         "camera_ids": None, "gaussian_ids": None, "radii": radii, "means2d": means2d, "depths": depths,
-        "conics": conics, "opacities": opac, "ray_ts": ray_ts, "ray_planes": ray_planes, "normals": normals,
+        "conics": conics, "opacities": opac_meta, "ray_ts": ray_ts, "ray_planes": ray_planes, "normals": normals,
         "tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
         "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
         "height": height, "tile_size": tile_size, "n_cameras": C,

@@ -92,28 +92,48 @@ int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t
  * Inputs are first packed: geom[C*N,16] (rs_pack_geom) and colours padded to DP = rs_raster_padded_channels(D)
  * channels (rs_pack_colors; colours may be [C*N,D] (color_per_cam=1) or [N,D] shared by all cameras). */
 int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the host */
-int rs_pack_geom(const float* means2d, const float* conics, const float* opacities /* [C*N] */, const float* ray_ts,
-                 const float* ray_planes, const float* normals, const int32_t* radii /* NULL ok */,
-                 long long n_elems, float* geom, void* stream);
+int rs_pack_geom(const float* means2d, const float* conics,
+                 const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
+                 const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,
+                 int C, int N, const float* ray_ts, const float* ray_planes, const float* normals,
+                 const int32_t* radii /* NULL ok */, float* geom /* [C*N,16] */, void* stream);
 int rs_pack_colors(const float* colors, long long rows, int D, int DP, float* out, void* stream);
-int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+/* ed_channel >= 0: that output channel is divided by max(alpha, 1e-10) (the "ED" render modes); -1: none. */
+int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D, int ed_channel,
                      const float* backgrounds /* [C,D] or NULL */, const float* Ks, int C, int N, int width,
                      int height, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
                      long long M, float* out_colors /* [C,H,W,D] */, float* out_alphas /* [C,H,W] */,
                      float* out_expected_depths, float* out_median_depths, float* out_normals /* [C,H,W,3] */,
                      float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream);
-/* geom_grad[C*N,16] and color_grad[rows,DP] must be zero-filled by the caller; gradients are accumulated. */
-int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D,
+/* Gradient record geom_grad[C*N,16] = (gx gy | ga gb gc | go | g_ray_t g_rpx g_rpy | gnx gny gnz | colour 0..3);
+ * geom_grad, color_grad[rows,DP] (only needed when DP > 4) and abs_grad[C*N,2] (NULL = absgrad off) must be
+ * zero-filled by the caller; gradients are accumulated.  out_colors is only read when ed_channel >= 0. */
+int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D, int ed_channel,
                      const float* backgrounds, const float* Ks, int C, int N, int width, int height, int tile_w,
                      int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids, long long M,
-                     const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
-                     const float* v_colors, const float* v_alphas, const float* v_expected_depths,
-                     const float* v_median_depths, const float* v_normals, float* geom_grad, float* color_grad,
-                     void* stream);
-int rs_unpack_geom_grad(const float* geom_grad, long long n_elems, float* v_means2d,
-                        float* v_means2d_abs /* NULL ok */, float* v_conics, float* v_opacities, float* v_ray_ts,
-                        float* v_ray_planes, float* v_normals, void* stream);
+                     const float* out_colors, const float* transmittance, const int32_t* last_ids,
+                     const int32_t* median_ids, const float* v_colors, const float* v_alphas,
+                     const float* v_expected_depths, const float* v_median_depths, const float* v_normals,
+                     float* geom_grad, float* color_grad, float* abs_grad, void* stream);
+/* Splits the gradient record into the per-input gradients; undoes the opacity * compensation fusion
+ * (v_compensations[C,N] = go * opacity, v_opacities = go * compensation, summed over cameras when the
+ * opacities are [N]); v_colors4 (NULL ok) receives the colour gradient when the colours have <= 4 channels. */
+int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad /* NULL ok */, int C, int N,
+                        const float* opacities, int opac_per_cam, const float* compensations /* NULL ok */,
+                        float* v_means2d, float* v_means2d_abs /* NULL ok */, float* v_conics, float* v_opacities,
+                        float* v_compensations /* NULL ok */, float* v_ray_ts, float* v_ray_planes,
+                        float* v_normals, float* v_colors4 /* NULL ok */, int color_per_cam, int D, void* stream);
 int rs_unpack_colors_grad(const float* color_grad, long long rows, int D, int DP, float* out, void* stream);
+
+/* ---- fused view-dependent colours: replaces, inside rasterization(), inverse(viewmats) -> dirs ->
+ * spherical_harmonics(masks = radii > 0) -> +0.5 -> clamp_min(0) -> cat(depth) and its autograd.
+ * colors4[C,N,4] = (rgb, depth or 0); coeffs[N,K,3] are shared by all cameras. */
+int rs_sh_colors_fwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                     const float* viewmats, const int32_t* radii, const float* depths /* NULL ok */,
+                     float* colors4, void* stream);
+int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                     const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,
+                     float* v_coeffs, float* v_means, float* v_depths /* NULL unless has_depth */, void* stream);
 
 /* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
  * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and

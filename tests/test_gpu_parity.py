@@ -475,3 +475,37 @@ def test_fused_loss_matches_reference_glue(cuda_dev, use_dn, with_bg, D):
     for k in leaves:
         ok, msg = grad_close_report("v_" + k, gpu[k].grad, cpu[k].grad, rel=1e-3, floor=1e-9)
         assert ok, msg
+
+
+@pytest.mark.parametrize("degree,with_depth,views", [(0, False, 1), (2, True, 2), (3, True, 1), (3, False, 3)])
+def test_sh_colors_fused(cuda_dev, degree, with_depth, views):
+    """csrc/colors.cu against the chain it replaces inside rasterization():
+    inverse(viewmats) -> dirs -> spherical_harmonics(masks) -> +0.5 -> clamp_min(0) -> cat(depth)."""
+    from gsplat.cuda._wrapper import sh_colors
+    cfg, gs, vm, Ks = small_scene(n=5000, views=views, spread=1.8)
+    means, quats, scales, _, sh = scenes.activate(gs, 3)
+    sh = sh * 6.0          # large coefficients so that the clamp at 0 is active for some Gaussians
+    radii, _, depths = O.fully_fused_projection(means, quats, scales, vm, Ks, cfg.width, cfg.height)[:3]
+    mc, sc = means.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+    dc = depths.clone().requires_grad_(True)
+    campos = torch.linalg.inv(vm)[:, :3, 3]
+    ref = O.spherical_harmonics(degree, mc[None] - campos[:, None], sc[None].expand(views, -1, -1, -1),
+                                masks=(radii > 0).all(-1))
+    ref = torch.clamp_min(ref + 0.5, 0.0)
+    ref = torch.cat([ref, dc[..., None] if with_depth else torch.zeros(views, cfg.n_gaussians, 1)], dim=-1)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4))
+    (ref * w).sum().backward()
+    mg, sg = means.to(cuda_dev).requires_grad_(True), sh.to(cuda_dev).requires_grad_(True)
+    dg = depths.to(cuda_dev).requires_grad_(True)
+    got = sh_colors(degree, mg, sg, vm.to(cuda_dev), radii.to(cuda_dev), dg if with_depth else None)
+    (got * w.to(cuda_dev)).sum().backward()
+    assert 0.02 < float((ref[..., :3] == 0).float().mean()) < 0.9
+    ok, msg = close_report("colors4", got, ref, atol=2e-5, rtol=1e-4)
+    assert ok, msg
+    ok, msg = grad_close_report("v_coeffs", sg.grad, sc.grad, rel=1e-4)
+    assert ok, msg
+    ok, msg = grad_close_report("v_means", mg.grad, mc.grad, rel=2e-3)
+    assert ok, msg
+    if with_depth:
+        ok, msg = grad_close_report("v_depths", dg.grad, dc.grad, rel=1e-6)
+        assert ok, msg
