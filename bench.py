@@ -378,17 +378,30 @@ def main():
         "gpu_launches": launches,
     }
     if rank == 0:
-        st, M, D = stage_times(wl)
+        # per-kernel device time measured INSIDE real steps (same inputs, same cache state): the library
+        # brackets every entry point with CUDA events on the launching stream
+        lib.rs_timing_enable(1)
+        n_t = 5
+        for _ in range(n_t):
+            resident()
+        torch.cuda.synchronize(device)
+        spans = backend.timing_collect()
+        lib.rs_timing_enable(0)
+        st = {k: v[0] / n_t for k, v in spans.items()}
+        M = int(wl.last_meta["flatten_ids"].numel())
+        D = 4
         peak, how = measured_peaks()
         P = wl.cfg.width * wl.cfg.height
-        key = "rasterize_bwd(+unpack)"
+        key = "rs_rasterize_bwd"
         alg_bytes = M * (52 + 4 * D) + P * (4 * D + 36)           # SURVEY 8d, without the atomic-commit term
         achieved = alg_bytes / (st[key] * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd_kernel<4,256>", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": how,
-                            "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
-                            "note": "compositing is FP32/issue-bound, not HBM-bound (SURVEY 8d); see DESIGN.md"}
-        line["stage_ms"] = {k: round(v, 4) for k, v in st.items()}
+        line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd_kernel<4,256,false>", "achieved": achieved,
+                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": how, "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
+                            "note": "compositing is FP32-issue-bound, not HBM-bound (SURVEY 8d; ncu: issue-active "
+                                    "~80%, DRAM ~2%); see DESIGN.md and profiles/"}
+        line["stage_ms"] = {k: round(v, 4) for k, v in sorted(st.items(), key=lambda kv: -kv[1])}
+        line["stage_ms"]["sum_of_library_kernels"] = round(sum(st.values()), 4)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, sample, _ = cpu_baseline_sample(args.config, threads)

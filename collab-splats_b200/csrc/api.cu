@@ -23,3 +23,67 @@ extern "C" const char* rs_error_string(int status) {
     default: return "unknown status";
   }
 }
+
+// ------------------------------------------------------------------------------------------------ in-situ timing
+// Optional per-entry-point device timing: when enabled, every extern "C" launcher brackets its launches with a
+// pair of CUDA events on the launching stream.  rs_timing_collect() synchronises those events and returns the
+// accumulated milliseconds per entry point.  bench.py uses it to time each kernel *inside* the real step
+// (same inputs, same cache state) instead of in isolation.
+#include <string.h>
+namespace {
+constexpr int kMaxSpans = 4096;
+struct Span { const char* name; cudaEvent_t e0, e1; };
+Span g_spans[kMaxSpans];
+int g_n_spans = 0;
+int g_timing_on = 0;
+cudaEvent_t g_pool[2 * kMaxSpans];
+int g_pool_ready = 0;
+}  // namespace
+
+extern "C" void rs_timing_enable(int on) {
+  if (on && !g_pool_ready) {
+    for (int i = 0; i < 2 * kMaxSpans; ++i) cudaEventCreate(&g_pool[i]);
+    g_pool_ready = 1;
+  }
+  g_timing_on = on;
+  g_n_spans = 0;
+}
+
+extern "C" int rs_timing_begin(const char* name, void* stream) {
+  if (!g_timing_on || g_n_spans >= kMaxSpans) return -1;
+  const int i = g_n_spans++;
+  g_spans[i].name = name;
+  g_spans[i].e0 = g_pool[2 * i];
+  g_spans[i].e1 = g_pool[2 * i + 1];
+  cudaEventRecord(g_spans[i].e0, (cudaStream_t)stream);
+  return i;
+}
+
+extern "C" void rs_timing_end(int span, void* stream) {
+  if (span >= 0) cudaEventRecord(g_spans[span].e1, (cudaStream_t)stream);
+}
+
+// Writes up to `cap` (name, total ms, calls) rows; returns the number of distinct names.  Resets the span list.
+extern "C" int rs_timing_collect(char* names /* cap x 48 bytes */, float* ms, int* calls, int cap) {
+  int n = 0;
+  for (int i = 0; i < g_n_spans; ++i) {
+    cudaEventSynchronize(g_spans[i].e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_spans[i].e0, g_spans[i].e1);
+    int k = 0;
+    for (; k < n; ++k)
+      if (strncmp(names + 48 * k, g_spans[i].name, 47) == 0) break;
+    if (k == n) {
+      if (n >= cap) continue;
+      strncpy(names + 48 * n, g_spans[i].name, 47);
+      names[48 * n + 47] = 0;
+      ms[n] = 0.f;
+      calls[n] = 0;
+      ++n;
+    }
+    ms[k] += t;
+    calls[k] += 1;
+  }
+  g_n_spans = 0;
+  return n;
+}

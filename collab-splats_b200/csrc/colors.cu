@@ -174,6 +174,7 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
 extern "C" int rs_sh_colors_fwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
                                 const float* viewmats, const int32_t* radii, const float* depths, float* colors4,
                                 void* stream) {
+  RsSpan span__("rs_sh_colors_fwd", stream);
   if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || C < 0 || N < 0) return RS_ERR_BAD_ARG;
   if (C == 0 || N == 0) return RS_OK;
   if (!means || !coeffs || !viewmats || !radii || !colors4) return RS_ERR_BAD_ARG;
@@ -188,6 +189,7 @@ extern "C" int rs_sh_colors_fwd(int degree, int K, int C, int N, const float* me
 extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* means, const float* coeffs,
                                 const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,
                                 float* v_coeffs, float* v_means, float* v_depths, void* stream) {
+  RsSpan span__("rs_sh_colors_bwd", stream);
   if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || C < 0 || N < 0) return RS_ERR_BAD_ARG;
   if (N == 0) return RS_OK;
   if (!means || !coeffs || !viewmats || !radii || !v_colors4 || !v_coeffs || !v_means || (has_depth && !v_depths))

@@ -20,6 +20,16 @@
 
 extern "C" void rs_set_last_cuda_error(int code);
 extern "C" void rs_count_launches(int n);
+extern "C" int rs_timing_begin(const char* name, void* stream);
+extern "C" void rs_timing_end(int span, void* stream);
+
+// RAII span for the optional in-situ timing (api.cu); no-op unless rs_timing_enable(1) was called
+struct RsSpan {
+  int id;
+  void* st;
+  RsSpan(const char* name, void* stream) : id(rs_timing_begin(name, stream)), st(stream) {}
+  ~RsSpan() { rs_timing_end(id, st); }
+};
 
 static inline int rs_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 

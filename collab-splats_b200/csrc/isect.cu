@@ -184,6 +184,7 @@ extern "C" int rs_tile_bits(int tile_w, int tile_h) { return tile_bits_for((long
 
 extern "C" int rs_isect_count(const float* means2d, const int32_t* radii, long long n_elems, int tile_w, int tile_h,
                               int32_t* tiles_per_gauss, void* stream) {
+  RsSpan span__("rs_isect_count", stream);
   if (n_elems < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
   if (n_elems == 0) return RS_OK;
   if (!means2d || !radii || !tiles_per_gauss) return RS_ERR_BAD_ARG;
@@ -200,6 +201,7 @@ extern "C" long long rs_cumsum_temp_bytes(long long n) {
 // inclusive prefix sum int32 -> int64; temp is caller-owned scratch of rs_cumsum_temp_bytes(n) bytes
 extern "C" int rs_cumsum_i32_i64(const int32_t* in, long long* out, long long n, void* temp, long long temp_bytes,
                                  void* stream) {
+  RsSpan span__("rs_cumsum_i32_i64", stream);
   if (n < 0) return RS_ERR_BAD_ARG;
   if (n == 0) return RS_OK;
   if (!in || !out || !temp || temp_bytes < rs_cumsum_temp_bytes(n)) return RS_ERR_BAD_ARG;
@@ -215,6 +217,7 @@ extern "C" int rs_cumsum_i32_i64(const int32_t* in, long long* out, long long n,
 extern "C" int rs_isect_emit(const float* means2d, const int32_t* radii, const float* depths,
                              const long long* cum_tiles, int C, int N, int tile_w, int tile_h, long long* isect_ids,
                              int32_t* flatten_ids, void* stream) {
+  RsSpan span__("rs_isect_emit", stream);
   if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
   if ((long long)C * N >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   if (C == 0 || N == 0) return RS_OK;
@@ -228,6 +231,7 @@ extern "C" int rs_isect_emit(const float* means2d, const int32_t* radii, const f
 
 extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, int tile_w, int tile_h,
                                 int32_t* offsets, void* stream) {
+  RsSpan span__("rs_offset_encode", stream);
   if (M < 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets) return RS_ERR_BAD_ARG;
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   long long n_tiles = (long long)tile_w * tile_h;

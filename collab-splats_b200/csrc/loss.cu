@@ -136,6 +136,7 @@ extern "C" int rs_rade_loss_fwd_bwd(const float* render, const float* alphas, co
                                     float w_l1, float w_exp, float w_med, int use_depth_normal, float* sums,
                                     float* v_render, float* v_alphas, float* v_exp_depth, float* v_med_depth,
                                     float* v_normals, void* stream) {
+  RsSpan span__("rs_rade_loss_fwd_bwd", stream);
   if (width <= 0 || height <= 0 || D < 3) return RS_ERR_BAD_ARG;
   if (!render || !alphas || !exp_depth || !med_depth || !normals || !gt_rgb_u8 || !sums || !v_render || !v_alphas ||
       !v_exp_depth || !v_med_depth || !v_normals)

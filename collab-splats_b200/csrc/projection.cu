@@ -97,7 +97,9 @@ project_fwd_kernel(const float* __restrict__ means, const float* __restrict__ qu
 
 // One thread per Gaussian, looping over cameras: the per-Gaussian gradients are summed over C in
 // registers (no atomics).  Camera gradients (optional) are warp-reduced then atomically added.
-__global__ void __launch_bounds__(PB)
+// Capped at 128 registers (two 256-thread CTAs per SM): the VJP is ~1500 instructions per element, so the
+// kernel is latency-bound rather than HBM-bound unless enough warps are resident.
+__global__ void __launch_bounds__(PB, 2)
 project_bwd_kernel(const float* __restrict__ means, const float* __restrict__ quats,
                    const float* __restrict__ scales, const float* __restrict__ viewmats,
                    const float* __restrict__ Ks, int C, int N, rs::ProjParams<float> pp,
@@ -185,6 +187,7 @@ extern "C" int rs_project_fwd(const float* means, const float* quats, const floa
                               float far_plane, float radius_clip, int calc_compensations, int32_t* radii,
                               float* means2d, float* depths, float* conics, float* compensations, float* ray_ts,
                               float* ray_planes, float* normals, void* stream) {
+  RsSpan span__("rs_project_fwd", stream);
   if (C < 0 || N < 0 || width <= 0 || height <= 0) return RS_ERR_BAD_ARG;
   if (C == 0 || N == 0) return RS_OK;
   if (!means || !quats || !scales || !viewmats || !Ks || !radii || !means2d || !depths || !conics || !ray_ts ||
@@ -204,6 +207,7 @@ extern "C" int rs_project_bwd(const float* means, const float* quats, const floa
                               const float* v_conics, const float* v_compensations, const float* v_ray_ts,
                               const float* v_ray_planes, const float* v_normals, float* v_means, float* v_quats,
                               float* v_scales, float* v_viewmats, void* stream) {
+  RsSpan span__("rs_project_bwd", stream);
   if (C < 0 || N < 0 || width <= 0 || height <= 0) return RS_ERR_BAD_ARG;
   if (N == 0) return RS_OK;
   if (!means || !quats || !scales || !viewmats || !Ks || !v_means2d || !v_conics || !v_means || !v_quats ||

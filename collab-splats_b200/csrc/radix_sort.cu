@@ -184,6 +184,7 @@ extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int en
 // Returns 0 if the sorted pairs are in (keys_b, vals_b), 1 if they are in (keys_a, vals_a), < 0 on error.
 extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
                              int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
+  RsSpan span__("rs_sort_pairs", stream);
   if (M < 0 || begin_bit < 0 || end_bit > 64) return RS_ERR_BAD_ARG;
   if (M >= (1ll << 30)) return RS_ERR_UNSUPPORTED;  // look-back words carry 30-bit counts
   if (M == 0 || end_bit <= begin_bit) return 1;

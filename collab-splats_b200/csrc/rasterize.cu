@@ -564,6 +564,7 @@ extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, int opac_per_cam,
                             const float* compensations, int C, int N, const float* ray_ts, const float* ray_planes,
                             const float* normals, const int32_t* radii, float* geom, void* stream) {
+  RsSpan span__("rs_pack_geom", stream);
   if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
   const long long n_elems = (long long)C * N;
   if (n_elems == 0) return RS_OK;
@@ -575,6 +576,7 @@ extern "C" int rs_pack_geom(const float* means2d, const float* conics, const flo
 }
 
 extern "C" int rs_pack_colors(const float* colors, long long rows, int D, int DP, float* out, void* stream) {
+  RsSpan span__("rs_pack_colors", stream);
   if (rows < 0 || D <= 0 || DP < D) return RS_ERR_BAD_ARG;
   if (rows == 0) return RS_OK;
   if (!colors || !out) return RS_ERR_BAD_ARG;
@@ -587,6 +589,7 @@ extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad
                                    float* v_means2d, float* v_means2d_abs, float* v_conics, float* v_opacities,
                                    float* v_compensations, float* v_ray_ts, float* v_ray_planes, float* v_normals,
                                    float* v_colors4, int color_per_cam, int D, void* stream) {
+  RsSpan span__("rs_unpack_geom_grad", stream);
   if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
   if ((long long)C * N == 0) return RS_OK;
   if (!geom_grad || !v_means2d || !v_conics || !v_opacities || !v_ray_ts || !v_ray_planes || !v_normals)
@@ -602,6 +605,7 @@ extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad
 }
 
 extern "C" int rs_unpack_colors_grad(const float* color_grad, long long rows, int D, int DP, float* out, void* stream) {
+  RsSpan span__("rs_unpack_colors_grad", stream);
   if (rows < 0 || D <= 0 || DP < D) return RS_ERR_BAD_ARG;
   if (rows == 0) return RS_OK;
   if (!color_grad || !out) return RS_ERR_BAD_ARG;
@@ -615,6 +619,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
                                 const int32_t* flatten_ids, long long M, float* out_colors, float* out_alphas,
                                 float* out_expected_depths, float* out_median_depths, float* out_normals,
                                 float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream) {
+  RsSpan span__("rs_rasterize_fwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
   a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;
@@ -646,6 +651,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
                                 const float* v_colors, const float* v_alphas, const float* v_expected_depths,
                                 const float* v_median_depths, const float* v_normals, float* geom_grad,
                                 float* color_grad, float* abs_grad, void* stream) {
+  RsSpan span__("rs_rasterize_bwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
   a.geom = (const float4*)geom; a.colors = colors_padded; a.backgrounds = backgrounds; a.Ks = Ks;

@@ -92,6 +92,7 @@ sh_bwd_kernel(int degree, int K, long long n_elems, long long n_rows, const floa
 
 extern "C" int rs_sh_fwd(int degree, int K, long long n_elems, long long n_coeff_rows, const float* dirs,
                          const float* coeffs, const uint8_t* masks, float* colors, void* stream) {
+  RsSpan span__("rs_sh_fwd", stream);
   if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || n_elems < 0 || n_coeff_rows <= 0)
     return n_elems == 0 ? RS_OK : RS_ERR_BAD_ARG;
   if (n_elems == 0) return RS_OK;
@@ -104,6 +105,7 @@ extern "C" int rs_sh_fwd(int degree, int K, long long n_elems, long long n_coeff
 extern "C" int rs_sh_bwd(int degree, int K, long long n_elems, long long n_coeff_rows, const float* dirs,
                          const float* coeffs, const uint8_t* masks, const float* v_colors, float* v_coeffs,
                          float* v_dirs, void* stream) {
+  RsSpan span__("rs_sh_bwd", stream);
   if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || n_elems < 0 || n_coeff_rows <= 0)
     return n_elems == 0 ? RS_OK : RS_ERR_BAD_ARG;
   if (n_elems == 0) return RS_OK;

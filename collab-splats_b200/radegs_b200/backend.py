@@ -25,6 +25,8 @@ _SIGNATURES = {
     "rs_error_string": (C.c_char_p, [_i]),
     "rs_last_cuda_error": (C.c_int, []),
     "rs_launch_count": (C.c_ulonglong, []),
+    "rs_timing_enable": (None, [_i]),
+    "rs_timing_collect": (_i, [C.c_char_p, _p, _p, _i]),
     "rs_project_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 8 + [_p]),
     "rs_project_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_p] * 7 + [_p] * 4 + [_p]),
     "rs_sh_fwd": (_i, [_i, _i, _ll, _ll, _p, _p, _p, _p, _p]),
@@ -50,7 +52,21 @@ _SIGNATURES = {
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 
-EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("rs_set_last_cuda_error", "rs_count_launches")
+EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("rs_set_last_cuda_error", "rs_count_launches", "rs_timing_begin",
+                                          "rs_timing_end")
+
+
+def timing_collect(cap: int = 64):
+    """{entry point: (total ms, calls)} accumulated since rs_timing_enable(1) / the last collect."""
+    lib = load()
+    names = C.create_string_buffer(48 * cap)
+    ms = (C.c_float * cap)()
+    calls = (C.c_int * cap)()
+    n = lib.rs_timing_collect(names, C.cast(ms, C.c_void_p), C.cast(calls, C.c_void_p), cap)
+    out = {}
+    for i in range(n):
+        out[names.raw[48 * i:48 * (i + 1)].split(b"\0", 1)[0].decode()] = (float(ms[i]), int(calls[i]))
+    return out
 
 
 def lib_path() -> Path:

@@ -38,6 +38,12 @@ int rs_last_cuda_error(void);
 void rs_set_last_cuda_error(int code);
 void rs_count_launches(int n);
 unsigned long long rs_launch_count(void); /* kernels launched through this library so far */
+/* Optional in-situ timing: when enabled every entry point brackets its launches with CUDA events on the launching
+ * stream; rs_timing_collect() synchronises them and returns (name[48], total ms, calls) per entry point. */
+void rs_timing_enable(int on);
+int rs_timing_begin(const char* name, void* stream);
+void rs_timing_end(int span, void* stream);
+int rs_timing_collect(char* names /* cap x 48 */, float* ms, int* calls, int cap);
 
 /* ---- projection: replaces gsplat-rade fully_fused_projection fwd (packed=False, pinhole).
  * means[N,3] quats[N,4] (wxyz, un-normalised) scales[N,3] viewmats[C,4,4] Ks[C,3,3] ->

@@ -7,8 +7,9 @@ $CMD > gpurun_out/profile_plain.log 2>&1 || { echo "plain run failed"; tail -20 
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:rasterize_ \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k 'regex:rasterize_|radix_scatter|project_bwd|sh_colors' \
     -o gpurun_out/prof_raster -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out
-tail -3 gpurun_out/ncu_launches.log gpurun_out/ncu_full.log
+tail -n 3 gpurun_out/ncu_launches.log; tail -n 3 gpurun_out/ncu_full.log
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo bench exit $?; cat gpurun_out/bench.json | head -c 3000
