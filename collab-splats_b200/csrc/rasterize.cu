@@ -464,41 +464,44 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         const bool valid = inside && idx <= last_id && sig >= 0.f && alpha >= RS_ALPHA_MIN;
         if (!__any_sync(RS_FULL_MASK, valid)) continue;
         const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
-        float gq[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) gq[k] = 0.f;
-        float vis = 0.f, ax = 0.f, ay = 0.f;
-        if (valid) {
-          const float ra = rs::fast_rcp(1.f - alpha);
-          T *= ra;  // transmittance in front of this Gaussian
-          vis = alpha * T;
-          const float tt = q2.x + q2.y * dx + q2.z * dy;
-          float w = v_dsum * tt + v_n0 * q3.x + v_n1 * q3.y + v_n2 * q3.z;
+        // Branch-free: invalid lanes behave as a Gaussian with alpha = 0 (ra = 1, vis = 0), so every gradient
+        // term below is an exact 0 for them and no zero-initialisation / divergent region is needed.
+        const float am = valid ? alpha : 0.f;
+        const float ra = rs::fast_rcp(1.f - am);
+        T *= ra;  // transmittance in front of this Gaussian
+        const float vis = am * T;
+        const float tt = q2.x + q2.y * dx + q2.z * dy;
+        float w = v_dsum * tt + v_n0 * q3.x + v_n1 * q3.y + v_n2 * q3.z;
+        {
           const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
 #pragma unroll
           for (int k = 0; k < DP / 4; ++k) {
             const float4 cc = cp[k];
             w += v_c[4 * k] * cc.x + v_c[4 * k + 1] * cc.y + v_c[4 * k + 2] * cc.z + v_c[4 * k + 3] * cc.w;
           }
-          const float v_alpha = T * w - R * ra + tfin_term * ra;
-          R += vis * w;
-          const float v_t = vis * v_dsum + (idx == med_id ? v_dmed : 0.f);
-          float v_sig = 0.f, v_o = 0.f;
-          if (oe <= RS_ALPHA_MAX) { v_sig = -alpha * v_alpha; v_o = ex * v_alpha; }
-          // d sigma / d(dx,dy) with the raw conic (a,b,c) = ln2 * (2 q1.x, q1.y, 2 q1.z)
-          const float vs2 = v_sig * RS_LN2;
-          const float gx = vs2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
-          const float gy = vs2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
-          const float hx = 0.5f * dx * v_sig, hy = 0.5f * dy * v_sig;
-          gq[0] = gx; gq[1] = gy;
-          gq[2] = hx * dx; gq[3] = 2.f * hx * dy; gq[4] = hy * dy; gq[5] = v_o;
-          gq[6] = v_t; gq[7] = v_t * dx; gq[8] = v_t * dy;
-          gq[9] = vis * v_n0; gq[10] = vis * v_n1; gq[11] = vis * v_n2;
-          if constexpr (DP == 4) {
-            gq[12] = vis * v_c[0]; gq[13] = vis * v_c[1]; gq[14] = vis * v_c[2]; gq[15] = vis * v_c[3];
-          }
-          ax = fabsf(gx); ay = fabsf(gy);
         }
+        const float v_alpha = T * w - R * ra + tfin_term * ra;
+        R += vis * w;
+        const float v_t = vis * v_dsum + ((valid && idx == med_id) ? v_dmed : 0.f);
+        const bool unclamped = valid && oe <= RS_ALPHA_MAX;
+        const float v_sig = unclamped ? -am * v_alpha : 0.f;
+        const float v_o = unclamped ? ex * v_alpha : 0.f;
+        // d sigma / d(dx,dy) with the raw conic (a,b,c) = ln2 * (2 q1.x, q1.y, 2 q1.z)
+        const float vs2 = v_sig * RS_LN2;
+        const float gx = vs2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
+        const float gy = vs2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
+        const float hx = 0.5f * dx * v_sig, hy = 0.5f * dy * v_sig;
+        float gq[16];
+        gq[0] = gx; gq[1] = gy;
+        gq[2] = hx * dx; gq[3] = 2.f * hx * dy; gq[4] = hy * dy; gq[5] = v_o;
+        gq[6] = v_t; gq[7] = v_t * dx; gq[8] = v_t * dy;
+        gq[9] = vis * v_n0; gq[10] = vis * v_n1; gq[11] = vis * v_n2;
+        if constexpr (DP == 4) {
+          gq[12] = vis * v_c[0]; gq[13] = vis * v_c[1]; gq[14] = vis * v_c[2]; gq[15] = vis * v_c[3];
+        } else {
+          gq[12] = gq[13] = gq[14] = gq[15] = 0.f;
+        }
+        const float ax = fabsf(gx), ay = fabsf(gy);
         const int id = __float_as_int(q2.w);  // flatten id carried by the record (s.ids is recycled concurrently)
         rs::warp_reduce_scatter<16>(gq, lane);
         {
