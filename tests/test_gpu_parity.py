@@ -509,3 +509,36 @@ def test_sh_colors_fused(cuda_dev, degree, with_depth, views):
     if with_depth:
         ok, msg = grad_close_report("v_depths", dg.grad, dc.grad, rel=1e-6)
         assert ok, msg
+
+
+@pytest.mark.parametrize("cfg_id", [2, 3])
+def test_full_size_adjoint_identity(cuda_dev, cfg_id):
+    """BASELINE config 2 (1M, 1080p, D=3) and config 3 (500k, 960x540, 3+64 feature channels) at full size.
+    The render is exactly linear in the colours, so forward and backward must satisfy the adjoint identity
+    <render(c), w> = <c, d<render,w>/dc> and additivity render(a+b) = render(a)+render(b) -- size-independent
+    checks of the wide-channel forward AND backward where the oracle would take hours."""
+    from gsplat.rendering import rasterization
+    cfg = scenes.BASELINE_CONFIGS[cfg_id]
+    gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
+    means, quats, scales, opac, _ = _gpu(scenes.activate(gs, cfg.sh_degree)[:5], cuda_dev)
+    D = 3 + cfg.n_features
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    ca = torch.rand(cfg.n_gaussians, D, device=cuda_dev, generator=g).requires_grad_(True)
+    cb = torch.rand(cfg.n_gaussians, D, device=cuda_dev, generator=g)
+    vmd, Kd = vm.to(cuda_dev), Ks.to(cuda_dev)
+
+    def render(c):
+        return rasterization(means, quats, scales, opac, c, vmd, Kd, cfg.width, cfg.height, packed=False,
+                             rasterize_mode="antialiased", return_depth_normal=True)[0]
+
+    ra = render(ca)
+    w = torch.randn(ra.shape, device=cuda_dev, generator=g)
+    lhs = (ra.double() * w.double()).sum()
+    (ra * w).sum().backward()
+    rhs = (ca.detach().double() * ca.grad.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 2e-4 * max(abs(lhs.item()), float((ra.abs() * w.abs()).sum()) * 1e-3), \
+        (lhs.item(), rhs.item())
+    with torch.no_grad():
+        rb, rab = render(cb), render(ca.detach() + cb)
+    assert float((rab - ra.detach() - rb).abs().max()) < 5e-5 * D ** 0.5
+    assert float(ra.detach().abs().max()) > 0.5
