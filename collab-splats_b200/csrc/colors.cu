@@ -109,12 +109,17 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
   rows_to_smem(s_rows, coeffs + (size_t)n0 * row, count, row, RS, t);
   __syncthreads();
   const int nb = (degree + 1) * (degree + 1);
-  float acc[48];
-#pragma unroll
-  for (int i = 0; i < 48; ++i) acc[i] = 0.f;
-  float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+  // Coefficient gradients accumulate in shared memory, not in 48 registers: the kernel is HBM-bound and needs
+  // the occupancy.  With one camera they overwrite the coefficients in place (every read of a row entry
+  // precedes its write); with several cameras they go to a second, zero-initialised row.
+  const bool in_place = (C == 1);
+  float* s_out = in_place ? s_rows : s_rows + CB * RS;
   const int n = n0 + t;
   if (t < count) {
+    float* o = s_out + t * RS;
+    if (!in_place)
+      for (int i = 0; i < row; ++i) o[i] = 0.f;
+    float vmx = 0.f, vmy = 0.f, vmz = 0.f;
     const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
     const float* cf = s_rows + t * RS;
     for (int c = 0; c < C; ++c) {
@@ -122,7 +127,7 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
       const float4 vc = __ldg(v_colors4 + e);
       if (has_depth) v_depths[e] = vc.w;
       const int2 rad = __ldg(radii + e);
-      if (!(rad.x > 0 && rad.y > 0)) continue;
+      const bool live = rad.x > 0 && rad.y > 0;  // masked entries contribute exact zeros
       float cx, cy, cz;
       camera_position(viewmats + c * 16, cx, cy, cz);
       const float x = mx - cx, y = my - cy, z = mz - cz;
@@ -135,14 +140,19 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
       for (int q = 0; q < 16; ++q)
         if (q < nb) { r += basis[q] * cf[q * 3]; g += basis[q] * cf[q * 3 + 1]; b += basis[q] * cf[q * 3 + 2]; }
       // clamp_min(sh + 0.5, 0): gradient passes where the un-clamped value is >= 0
-      const float vr = (r + 0.5f >= 0.f) ? vc.x : 0.f, vg = (g + 0.5f >= 0.f) ? vc.y : 0.f,
-                  vb = (b + 0.5f >= 0.f) ? vc.z : 0.f;
+      const float vr = (live && r + 0.5f >= 0.f) ? vc.x : 0.f, vg = (live && g + 0.5f >= 0.f) ? vc.y : 0.f,
+                  vb = (live && b + 0.5f >= 0.f) ? vc.z : 0.f;
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
         gq[q] = 0.f;
-        if (q < nb) {
-          acc[q * 3] += basis[q] * vr; acc[q * 3 + 1] += basis[q] * vg; acc[q * 3 + 2] += basis[q] * vb;
-          gq[q] = vr * cf[q * 3] + vg * cf[q * 3 + 1] + vb * cf[q * 3 + 2];
+        if (q < K) {
+          const float bq = q < nb ? basis[q] : 0.f;
+          if (q < nb) gq[q] = vr * cf[q * 3] + vg * cf[q * 3 + 1] + vb * cf[q * 3 + 2];
+          if (in_place) {
+            o[q * 3] = bq * vr; o[q * 3 + 1] = bq * vg; o[q * 3 + 2] = bq * vb;
+          } else {
+            o[q * 3] += bq * vr; o[q * 3 + 1] += bq * vg; o[q * 3 + 2] += bq * vb;
+          }
         }
       }
       float bx, by, bz;
@@ -152,19 +162,8 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
     }
     v_means[n * 3] = vmx; v_means[n * 3 + 1] = vmy; v_means[n * 3 + 2] = vmz;
   }
-  __syncthreads();  // everyone is done reading the coefficients: reuse the staging buffer for their gradients
-  if (t < count) {
-    float* o = s_rows + t * RS;
-#pragma unroll
-    for (int q = 0; q < 16; ++q)
-      if (q < K) {
-        o[q * 3] = q < nb ? acc[q * 3] : 0.f;
-        o[q * 3 + 1] = q < nb ? acc[q * 3 + 1] : 0.f;
-        o[q * 3 + 2] = q < nb ? acc[q * 3 + 2] : 0.f;
-      }
-  }
   __syncthreads();
-  smem_to_rows(s_rows, v_coeffs + (size_t)n0 * row, count, row, RS, t);
+  smem_to_rows(s_out, v_coeffs + (size_t)n0 * row, count, row, RS, t);
 }
 
 }  // namespace
@@ -194,7 +193,7 @@ extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* me
   if (N == 0) return RS_OK;
   if (!means || !coeffs || !viewmats || !radii || !v_colors4 || !v_coeffs || !v_means || (has_depth && !v_depths))
     return RS_ERR_BAD_ARG;
-  const size_t smem = sizeof(float) * CB * ((K * 3) | 1);
+  const size_t smem = (C == 1 ? 1 : 2) * sizeof(float) * CB * ((K * 3) | 1);
   sh_colors_bwd_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
       degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, (const float4*)v_colors4, has_depth, v_coeffs,
       v_means, v_depths);
