@@ -141,8 +141,11 @@ class Workload:
             return_depth_normal=True)
         self.last_meta = meta
         if self.fused_loss:   # csrc/loss.cu: L1 + depth-normal consistency, forward and gradients in one kernel
-            loss, _ = fused_rade_loss(render[0], alpha[0, ..., 0], exp_d[0, ..., 0], med_d[0, ..., 0], nrm[0], gt_u8,
-                                      self.fx, self.fy)
+            # C == 1: reshape (a free view in both directions) instead of indexing, whose backward would
+            # zero-fill and copy a full image per output
+            H, W = cfg.height, cfg.width
+            loss, _ = fused_rade_loss(render.view(H, W, -1), alpha.view(H, W), exp_d.view(H, W), med_d.view(H, W),
+                                      nrm.view(H, W, 3), gt_u8, self.fx, self.fy)
             return loss
         rgb = torch.clamp(render[0, ..., :3], 0.0, 1.0)
         l1 = (rgb - gt_u8.float() * (1.0 / 255.0)).abs().mean()
@@ -327,7 +330,8 @@ def main():
     torch.cuda.set_device(device)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=device)
+        from datetime import timedelta
+        dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))
     from radegs_b200 import backend
     lib = backend.load()
     warmup = max(args.warmup, 3)
@@ -388,7 +392,7 @@ def main():
         lib.rs_timing_enable(1)
         n_t = 5
         for _ in range(n_t):
-            resident()
+            wl.step_resident()          # rank 0 only: NO collective in here
         torch.cuda.synchronize(device)
         spans = backend.timing_collect()
         lib.rs_timing_enable(0)

@@ -18,9 +18,9 @@ typedef unsigned int u32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int ST = 256;            // threads per block
-constexpr int SI = 8;              // items per thread (8 -> ~60 registers, 4 CTAs/SM: the kernel is latency-bound,
-                                   // ncu showed 24 % warps active / 21 % DRAM at 16 items and 98 registers)
-constexpr int STILE = ST * SI;     // 2048 pairs per block
+// items per thread: 8 (64 registers, 4 CTAs/SM, 2048-pair tiles) or 16 (98 registers, 2 CTAs/SM, 4096-pair tiles);
+// selectable at run time (rs_sort_set_items) so both can be measured on the same box
+static int g_sort_items = 8;
 constexpr int SWARPS = ST / 32;
 constexpr int MAX_PASSES = 8;
 #define LB_AGG (1u << 30)
@@ -68,7 +68,8 @@ __device__ __forceinline__ u32 block_inclusive_scan(u32 v, u32* s_warp, int lane
   return v + off;
 }
 
-__global__ void __launch_bounds__(ST, 4)
+template <int SI>
+__global__ void __launch_bounds__(ST, (SI == 8 ? 4 : 2))
 radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
                      u32* __restrict__ vout, int M, int shift, u32 mask, const u32* __restrict__ ghist,
                      volatile u32* status, u32* ticket) {
@@ -77,6 +78,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
   __shared__ int s_gbase[RADIX];
   __shared__ u32 s_warp[SWARPS];
   __shared__ u32 s_tile;
+  constexpr int STILE = ST * SI;
   __shared__ __align__(16) u64 s_keys[STILE];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ticket, 1u);
@@ -123,32 +125,37 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
     s_cnt[w][t] = bcount;
     bcount += c;
   }
-  // ---- publish the block's digit count, then look back for the sum over all earlier tiles
+  // ---- publish the block's digit count early, so successors can aggregate it while this block reorders
   volatile u32* my_status = status + (size_t)tile * RADIX + t;
   *my_status = (tile == 0 ? LB_PREFIX : LB_AGG) | bcount;
   const u32 gh = __ldg(ghist + t);
   const u32 bin_incl = block_inclusive_scan(bcount, s_warp, lane, warp);
   const u32 gh_incl = block_inclusive_scan(gh, s_warp, lane, warp);
-  u32 excl_prev = 0;
-  for (int p = tile - 1; p >= 0; --p) {
-    volatile u32* ps = status + (size_t)p * RADIX + t;
-    u32 s;
-    do { s = *ps; } while ((s & LB_FLAGS) == 0u);
-    excl_prev += s & LB_VALUE;
-    if ((s & LB_FLAGS) == LB_PREFIX) break;
-  }
-  if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
   s_bin_start[t] = bin_incl - bcount;
-  s_gbase[t] = (int)((gh_incl - gh) + excl_prev) - (int)(bin_incl - bcount);
   __syncthreads();
-  // ---- reorder keys through shared memory, then coalesced writes
+  // ---- reorder keys through shared memory (needs only block-local offsets) BEFORE the look-back, so that the
+  //      predecessors have had time to publish their inclusive prefixes and the look-back chains stay short
 #pragma unroll
   for (int r = 0; r < SI; ++r) {
     const u32 d = (u32)((key[r] >> shift) & mask);
     pos[r] += s_bin_start[d] + s_cnt[warp][d];
     s_keys[pos[r]] = key[r];
   }
+  // ---- decoupled look-back (thread t <-> digit t): sum of the digit's counts over all earlier tiles
+  u32 excl_prev = 0;
+  for (int p = tile - 1; p >= 0; --p) {
+    const u32* ps = const_cast<const u32*>(status) + (size_t)p * RADIX + t;
+    u32 sv;
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv) : "l"(ps) : "memory");
+    } while ((sv & LB_FLAGS) == 0u);
+    excl_prev += sv & LB_VALUE;
+    if ((sv & LB_FLAGS) == LB_PREFIX) break;
+  }
+  if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
+  s_gbase[t] = (int)((gh_incl - gh) + excl_prev) - (int)(bin_incl - bcount);
   __syncthreads();
+  // ---- coalesced writes
   int out[SI];
 #pragma unroll
   for (int i = 0; i < SI; ++i) {
@@ -172,12 +179,14 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
 
 }  // namespace
 
-static long long sort_blocks(long long M) { return (M + STILE - 1) / STILE; }
+static long long sort_blocks(long long M, int items) { return (M + ST * items - 1) / (ST * items); }
+
+extern "C" void rs_sort_set_items(int items) { g_sort_items = (items == 16) ? 16 : 8; }
 
 extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit) {
   int npass = end_bit > begin_bit ? (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS : 0;
   if (npass > MAX_PASSES) npass = MAX_PASSES;
-  long long nb = sort_blocks(M > 0 ? M : 1);
+  long long nb = sort_blocks(M > 0 ? M : 1, 8);  // sized for the smaller tile, enough for either setting
   return (long long)MAX_PASSES * RADIX * 4 + 256 + (long long)npass * nb * RADIX * 4;
 }
 
@@ -203,20 +212,27 @@ extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys
     pi.shift[p] = p < npass ? sh : 0;
     pi.mask[p] = p < npass ? ((1u << nb) - 1u) : 0u;
   }
-  const long long nblocks = sort_blocks(M);
+  const int items = g_sort_items;
+  const long long nblocks = sort_blocks(M, items);
   cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)rs_sort_pairs_temp_bytes(M, begin_bit, end_bit), st);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
   u32* ghist = (u32*)temp;
   u32* tickets = (u32*)((char*)temp + MAX_PASSES * RADIX * 4);
   u32* status = (u32*)((char*)temp + MAX_PASSES * RADIX * 4 + 256);
   int hist_blocks = (int)(nblocks < 148 * 8 ? nblocks : 148 * 8);
+  const long long status_stride = sort_blocks(M, 8) * RADIX;
   radix_hist_kernel<<<hist_blocks, ST, 0, st>>>((const u64*)keys_a, M, pi, ghist);
   u64* ka = (u64*)keys_a; u64* kb = (u64*)keys_b;
   u32* va = (u32*)vals_a; u32* vb = (u32*)vals_b;
   for (int p = 0; p < npass; ++p) {
-    radix_scatter_kernel<<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
-                                                          ghist + p * RADIX, status + (size_t)p * nblocks * RADIX,
-                                                          tickets + p);
+    if (items == 16)
+      radix_scatter_kernel<16><<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
+                                                                ghist + p * RADIX, status + (size_t)p * status_stride,
+                                                                tickets + p);
+    else
+      radix_scatter_kernel<8><<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
+                                                               ghist + p * RADIX, status + (size_t)p * status_stride,
+                                                               tickets + p);
     u64* tk = ka; ka = kb; kb = tk;
     u32* tv = va; va = vb; vb = tv;
   }

@@ -355,6 +355,7 @@ class _RasterizeToPixels(torch.autograd.Function):
                    ed_channel, colors.shape)
         ctx.means2d_ref = means2d if absgrad else None
         ctx.mark_non_differentiable(last_ids, median_ids)
+        ctx.set_materialize_grads(False)   # missing output gradients arrive as None (handled by z() below)
         return out_colors, out_alphas, out_dexp, out_dmed, out_normals, last_ids, median_ids
 
     @staticmethod

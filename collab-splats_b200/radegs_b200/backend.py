@@ -38,6 +38,7 @@ _SIGNATURES = {
     "rs_isect_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),
     "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
+    "rs_sort_set_items": (None, [_i]),
     "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_raster_padded_channels": (_i, [_i]),
     "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),

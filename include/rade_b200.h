@@ -91,6 +91,7 @@ int rs_offset_encode(const long long* sorted_isect_ids, long long M, int C, int 
  * Stable, ascending, on key bits [begin_bit,end_bit).  Clobbers both buffer pairs.
  * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */
 long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit);
+void rs_sort_set_items(int items_per_thread); /* tuning knob: 8 (default) or 16 keys per thread */
 int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
                   int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream);
 
