@@ -248,6 +248,43 @@ def stage_times(wl: Workload, reps: int = 5):
     return out, M, 4
 
 
+def fp32_accounting(wl, lib, backend, st, device):
+    """FP32 roofline of the compositing kernels: algorithmic flops 12*Q + (16+2D)*Qc forward and
+    14*Q' + (60+6D)*Qc backward over the measured in-step durations, against a sustained FFMA probe run here."""
+    counters = torch.zeros(4, device=device, dtype=torch.int64)
+    lib.rs_raster_set_stats(backend.ptr(counters))
+    with torch.no_grad():
+        wl.forward_loss(wl.viewmat, wl.K, wl.gt)          # instrumented forward, never timed
+    lib.rs_raster_set_stats(None)
+    Q, Qc, evals, blends = [int(v) for v in counters.tolist()]
+    meta = wl.last_meta
+    D = 4
+    flops_fwd = 12 * Q + (16 + 2 * D) * Qc
+    flops_bwd = 14 * Q + (60 + 6 * D) * Qc               # Q' <= Q: pairs up to the last contributor
+    probe_out = torch.zeros(1, device=device)
+    blocks, iters = 148 * 8, 4096
+    best = None
+    for _ in range(5):
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        backend.check(lib.rs_fma_peak_probe(blocks, iters, backend.ptr(probe_out), backend.stream_ptr(device)), "probe")
+        e1.record()
+        torch.cuda.synchronize(device)
+        t = e0.elapsed_time(e1)
+        best = t if best is None else min(best, t)
+    peak = blocks * 256 * iters * 32 / (best * 1e-3) / 1e12
+    f = flops_fwd / (st["rs_rasterize_fwd"] * 1e-3) / 1e12
+    b = flops_bwd / (st["rs_rasterize_bwd"] * 1e-3) / 1e12
+    return {"Q_pairs_visited_by_a_per_pixel_loop": Q, "Qc_pairs_blended": Qc, "warp_evaluations": evals,
+            "warp_evaluations_blending": blends, "fwd_algorithmic_tflops": round(f, 2),
+            "bwd_algorithmic_tflops": round(b, 2), "fma_probe_tflops": round(peak, 2),
+            "fwd_frac_of_probe": round(f / peak, 3), "bwd_frac_of_probe": round(b / peak, 3),
+            "note": "algorithmic flops count every pair the reference's per-pixel loop visits (SURVEY 8d); the "
+                    "kernels skip most of them with the warp-level footprint test, so this is work-equivalent "
+                    "throughput, not executed flops"}
+
+
 def cpu_baseline_sample(cfg_id: int, threads: int):
     """CPU oracle (a restatement of the reference path, kind 'port') on a bounded sample of the workload: all
     Gaussians projected, a central 256x144 window of the view composited, fwd + loss + bwd."""
@@ -409,6 +446,7 @@ def main():
                             "peak_source": how, "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
                             "note": "compositing is FP32-issue-bound, not HBM-bound (SURVEY 8d; ncu: issue-active "
                                     "~80%, DRAM ~2%); see DESIGN.md and profiles/"}
+        line["fp32"] = fp32_accounting(wl, lib, backend, st, device)
         line["stage_ms"] = {k: round(v, 4) for k, v in sorted(st.items(), key=lambda kv: -kv[1])}
         line["stage_ms"]["sum_of_library_kernels"] = round(sum(st.values()), 4)
         if world == 1 and not args.no_cpu_baseline:

@@ -87,3 +87,28 @@ extern "C" int rs_timing_collect(char* names /* cap x 48 bytes */, float* ms, in
   g_n_spans = 0;
   return n;
 }
+
+// ------------------------------------------------------------------------------------------------ FP32 peak probe
+// Sustained FP32 FMA throughput of this device (the denominator for the compositing kernels' FP32 roofline,
+// BASELINE.md section 1): 16 independent FFMA chains per thread, 2 flops per FFMA.
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* out) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (threadIdx.x + i);
+  const float b = 1.000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], b, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;  // never true: keeps the chains alive
+}
+
+// Launches the probe; flops executed = blocks * 256 * iters * 16 * 2.  The caller times it with CUDA events.
+extern "C" int rs_fma_peak_probe(int blocks, int iters, float* out, void* stream) {
+  if (blocks <= 0 || iters <= 0 || !out) return RS_ERR_BAD_ARG;
+  fma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+  RS_RETURN_LAST_ERROR();
+}

@@ -194,6 +194,10 @@ extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* me
   if (!means || !coeffs || !viewmats || !radii || !v_colors4 || !v_coeffs || !v_means || (has_depth && !v_depths))
     return RS_ERR_BAD_ARG;
   const size_t smem = (C == 1 ? 1 : 2) * sizeof(float) * CB * ((K * 3) | 1);
+  if (smem > 48 * 1024) {  // two staging rows at K = 16 need the opt-in shared-memory limit
+    cudaError_t e = cudaFuncSetAttribute(sh_colors_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  }
   sh_colors_bwd_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
       degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, (const float4*)v_colors4, has_depth, v_coeffs,
       v_means, v_depths);

@@ -166,6 +166,8 @@ struct RasterArgs {
   float* geom_grad;    // [C*N][16]  (layout: see unpack_geom_grad_kernel)
   float* color_grad;   // [color_rows][DP]  (DP > 4 only; DP == 4 colours travel in the geometry record)
   float* abs_grad;     // [C*N][2] or null
+  unsigned long long* stats;  // forward, optional: {Q pairs a per-pixel loop would visit, Qc contributing pairs,
+                              //                     warp evaluations, warp evaluations that blended}
 };
 
 template <int DP, int BATCH> struct Smem {
@@ -229,7 +231,7 @@ __device__ __forceinline__ float inv_ray_len(const RasterArgs& a, int cam, float
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int DP, int BATCH>
+template <int DP, int BATCH, bool STATS>
 __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
 #pragma unroll
   for (int k = 0; k < DP; ++k) acc[k] = 0.f;
   int last_id = start - 1, med_id = -1;
+  int st_contrib = 0, st_term = -1, st_evals = 0, st_blend = 0;  // STATS only
 
   const int nb = (end - start + BATCH - 1) / BATCH;
   if (nb > 0) {
@@ -285,11 +288,16 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
           const float dx = q0.x - px, dy = q0.y - py;
           const float sig = q1.x * dx * dx + q1.z * dy * dy + q1.y * dx * dy;
           const float alpha = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
+          if constexpr (STATS) {
+            ++st_evals;
+            st_blend += __any_sync(RS_FULL_MASK, sig >= 0.f && alpha >= RS_ALPHA_MIN && T * (1.f - alpha) > RS_T_STOP);
+          }
           if (sig >= 0.f && alpha >= RS_ALPHA_MIN) {
             const float nT = T * (1.f - alpha);
             if (!(nT > RS_T_STOP)) {
-              if (T != 0.f) { T_out = T; T = 0.f; }  // terminate: this Gaussian is not blended
+              if (T != 0.f) { T_out = T; T = 0.f; if constexpr (STATS) st_term = base_idx + jj; }  // terminate
             } else {
+              if constexpr (STATS) ++st_contrib;
               const float vis = alpha * T;
               const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
               const float tt = q2.x + q2.y * dx + q2.z * dy;
@@ -318,6 +326,22 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
     if (b + 2 < nb && t < BATCH) s.ids[b & 1][t] = next_id;  // batch b's ids are dead (gather issued last iteration)
   }
   rs::cp_async_wait_all();
+
+  if constexpr (STATS) {
+    // Q: list entries a per-pixel loop (the reference's) visits = up to and including the terminating Gaussian,
+    // or the whole list if the pixel never saturates;  Qc: pairs that were blended
+    unsigned long long q = 0, qc = 0;
+    if (c.inside) { q = (unsigned long long)((st_term >= 0 ? st_term + 1 : end) - start); qc = (unsigned long long)st_contrib; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      q += __shfl_xor_sync(RS_FULL_MASK, q, d);
+      qc += __shfl_xor_sync(RS_FULL_MASK, qc, d);
+    }
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, q); atomicAdd(a.stats + 1, qc);
+      atomicAdd(a.stats + 2, (unsigned long long)st_evals); atomicAdd(a.stats + 3, (unsigned long long)st_blend);
+    }
+  }
 
   if (c.inside) {
     if (T == 0.f) T = T_out;  // terminated pixel: transmittance in front of the Gaussian that stopped it
@@ -525,14 +549,23 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ launch
-template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
+template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
   const size_t smem = sizeof(Smem<DP, B>);
-  cudaError_t e = cudaFuncSetAttribute(rasterize_fwd_kernel<DP, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_fwd_kernel<DP, B, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
-  rasterize_fwd_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  rasterize_fwd_kernel<DP, B, STATS><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
+template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
+  if constexpr (DP == 4) {
+    if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
+  }
+  return launch_fwd2<DP, false>(a, st);
+}
+
+static unsigned long long* g_raster_stats = nullptr;
 template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
   const size_t smem = sizeof(Smem<DP, B>);
@@ -563,6 +596,11 @@ bool check_common(const RasterArgs& a) {
 }  // namespace
 
 extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
+
+// Work counters for the roofline arithmetic (bench.py): while `dev_counters` (4 x u64, device, zeroed by the caller)
+// is set, forward launches with <= 4 colour channels run an instrumented kernel that adds
+// {Q, Qc, warp evaluations, blending warp evaluations} to it.  Pass NULL to switch back to the normal kernel.
+extern "C" void rs_raster_set_stats(unsigned long long* dev_counters) { g_raster_stats = dev_counters; }
 
 extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, int opac_per_cam,
                             const float* compensations, int C, int N, const float* ray_ts, const float* ray_planes,
@@ -632,6 +670,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
+  a.stats = g_raster_stats;
   if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
     return RS_ERR_BAD_ARG;
   if (ed_channel >= D) return RS_ERR_BAD_ARG;

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "rs_last_cuda_error": (C.c_int, []),
     "rs_launch_count": (C.c_ulonglong, []),
     "rs_timing_enable": (None, [_i]),
+    "rs_fma_peak_probe": (_i, [_i, _i, _p, _p]),
     "rs_timing_collect": (_i, [C.c_char_p, _p, _p, _i]),
     "rs_project_fwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_i] + [_p] * 8 + [_p]),
     "rs_project_bwd": (_i, [_p] * 5 + [_i] * 4 + [_f] * 4 + [_p] * 7 + [_p] * 4 + [_p]),
@@ -41,6 +42,7 @@ _SIGNATURES = {
     "rs_sort_set_items": (None, [_i]),
     "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_raster_padded_channels": (_i, [_i]),
+    "rs_raster_set_stats": (None, [_p]),
     "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rs_pack_colors": (_i, [_p, _ll, _i, _i, _p, _p]),
     "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_p]),

@@ -44,6 +44,8 @@ void rs_timing_enable(int on);
 int rs_timing_begin(const char* name, void* stream);
 void rs_timing_end(int span, void* stream);
 int rs_timing_collect(char* names /* cap x 48 */, float* ms, int* calls, int cap);
+/* FP32 FMA throughput probe: executes blocks*256*iters*32 flops; time it with events on `stream`. */
+int rs_fma_peak_probe(int blocks, int iters, float* out, void* stream);
 
 /* ---- projection: replaces gsplat-rade fully_fused_projection fwd (packed=False, pinhole).
  * means[N,3] quats[N,4] (wxyz, un-normalised) scales[N,3] viewmats[C,4,4] Ks[C,3,3] ->
@@ -99,6 +101,9 @@ int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t
  * Inputs are first packed: geom[C*N,16] (rs_pack_geom) and colours padded to DP = rs_raster_padded_channels(D)
  * channels (rs_pack_colors; colours may be [C*N,D] (color_per_cam=1) or [N,D] shared by all cameras). */
 int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the host */
+/* Work counters for roofline arithmetic: while set, forward launches with <= 4 channels run an instrumented
+ * kernel adding {Q visited pairs, Qc blended pairs, warp evaluations, blending warp evaluations} (4 x u64). */
+void rs_raster_set_stats(unsigned long long* dev_counters);
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
                  const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,
