@@ -248,6 +248,51 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
 
 
 @torch.no_grad()
+def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int,
+                            tile_height: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go, bit-identical to calling the two (tests
+    check it), through the tile-partitioned path of csrc/tilesort.cu: per-tile histogram -> offsets, atomic-slot
+    emission into tile segments, per-tile shared-memory sort.  Falls back to the radix path when a tile holds
+    more than ``rs_tile_sort_max_segment()`` intersections.  One device->host read (M and the longest segment).
+    -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32."""
+    if tile_size != TILE_SIZE:
+        raise NotImplementedError("tile_size must be 16")
+    lib = _be.load()
+    C, N = depths.shape
+    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
+    _need_cuda(means2d, radii, depths)
+    dev = means2d.device
+    means2d, depths = _c(means2d), _c(depths)
+    radii = _c(radii, torch.int32)
+    T = C * tile_width * tile_height
+    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
+    counts = torch.zeros(T, device=dev, dtype=torch.int32)
+    offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
+    cursors = torch.empty(T, device=dev, dtype=torch.int32)
+    totals = torch.empty(2, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        st = _be.stream_ptr(dev)
+        _be.check(lib.rs_isect_tile_count(_be.ptr(means2d), _be.ptr(radii), C, N, tile_width, tile_height,
+                                          _be.ptr(tiles), _be.ptr(counts), st), "rs_isect_tile_count")
+        _be.check(lib.rs_isect_tile_scan(_be.ptr(counts), T, _be.ptr(offsets), _be.ptr(cursors), _be.ptr(totals), st),
+                  "rs_isect_tile_scan")
+        M, longest = (int(v) for v in totals.tolist())
+        if longest > lib.rs_tile_sort_max_segment():
+            _, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)
+            return tiles, ids, flat, offsets
+        ids = torch.empty(M, device=dev, dtype=torch.int64)
+        flat = torch.empty(M, device=dev, dtype=torch.int32)
+        if M == 0:
+            return tiles, ids, flat, offsets
+        pairs = torch.empty(M, device=dev, dtype=torch.int64)
+        _be.check(lib.rs_isect_tile_emit(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), C, N, tile_width,
+                                         tile_height, _be.ptr(cursors), _be.ptr(pairs), st), "rs_isect_tile_emit")
+        _be.check(lib.rs_isect_tile_sort(_be.ptr(pairs), _be.ptr(offsets), C, tile_width, tile_height, M, longest,
+                                         _be.ptr(ids), _be.ptr(flat), st), "rs_isect_tile_sort")
+    return tiles, ids, flat, offsets
+
+
+@torch.no_grad()
 def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
     """Same call as gsplat ``isect_offset_encode``: -> offsets [C, tile_height, tile_width] i32."""
     lib = _be.load()

@@ -16,8 +16,8 @@ from typing import Dict, Optional, Tuple
 import torch
 from torch import Tensor
 
-from .cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles, rasterize_to_pixels,
-                            sh_colors, spherical_harmonics)
+from .cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles, isect_tiles_and_offsets,
+                            rasterize_to_pixels, sh_colors, spherical_harmonics)
 
 MAX_CHANNELS_PER_PASS = 72
 
@@ -122,9 +122,8 @@ def rasterization(
     # ---- tile intersection, sort, offsets
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height,
-                                                          packed=False, n_cameras=C)
-    isect_offsets = isect_offset_encode(isect_ids, C, tile_width, tile_height)
+    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
+        means2d, radii, depths, tile_size, tile_width, tile_height)
 
     # ---- compositing (one pass up to 72 channels; wider colours are split, geometry comes from the first pass).
     # The "ED" normalisation (depth channel / alpha) runs in the kernel epilogue.

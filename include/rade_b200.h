@@ -89,6 +89,20 @@ int rs_isect_emit(const float* means2d, const int32_t* radii, const float* depth
 int rs_offset_encode(const long long* sorted_isect_ids, long long M, int C, int tile_w, int tile_h,
                      int32_t* offsets /* [C,tile_h,tile_w] */, void* stream);
 
+/* ---- tile-partitioned fast path for isect_tiles(sort=True) + isect_offset_encode (same outputs, bit for bit):
+ * per-tile histogram -> exclusive scan = tile offsets -> atomic-slot emission of (depth<<32 | flatten id) into the
+ * tile's segment -> per-tile shared-memory sort.  tile_counts must be zero-filled; totals_dev = {M, longest
+ * segment}; rs_isect_tile_sort needs longest segment <= rs_tile_sort_max_segment(), else use rs_sort_pairs. */
+int rs_tile_sort_max_segment(void);
+int rs_isect_tile_count(const float* means2d, const int32_t* radii, int C, int N, int tile_w, int tile_h,
+                        int32_t* tiles_per_gauss, int32_t* tile_counts, void* stream);
+int rs_isect_tile_scan(const int32_t* tile_counts, int n_total_tiles, int32_t* offsets, int32_t* cursors,
+                       long long* totals_dev, void* stream);
+int rs_isect_tile_emit(const float* means2d, const int32_t* radii, const float* depths, int C, int N, int tile_w,
+                       int tile_h, int32_t* cursors, unsigned long long* pairs, void* stream);
+int rs_isect_tile_sort(const unsigned long long* pairs, const int32_t* offsets, int C, int tile_w, int tile_h,
+                       long long M, int max_segment, long long* isect_ids, int32_t* flatten_ids, void* stream);
+
 /* ---- radix sort: replaces cub::DeviceRadixSort::SortPairs inside isect_tiles(sort=True).
  * Stable, ascending, on key bits [begin_bit,end_bit).  Clobbers both buffer pairs.
  * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */

@@ -569,3 +569,25 @@ def test_multi_camera_batch_equals_single_camera_calls(cuda_dev):
     for nm, a, b in zip(("means", "quats", "scales", "opacities", "sh"), batch, single):
         ok, msg = grad_close_report("v_" + nm, a.grad, b.grad, rel=1e-3)
         assert ok, msg
+
+
+@pytest.mark.parametrize("views,w,h,n,boost", [(1, 160, 96, 6000, 1.2), (3, 250, 130, 5000, 1.2), (1, 64, 48, 20000, 2.0)])
+def test_tile_partitioned_isect_matches_radix_path(cuda_dev, views, w, h, n, boost):
+    """csrc/tilesort.cu (the path rasterization() uses) against the radix path and the oracle: bit-exact."""
+    from gsplat.cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles,
+                                      isect_tiles_and_offsets)
+    cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views, spread=1.3, scale_boost=boost)
+    means, quats, scales, _, _ = scenes.activate(gs, 3)
+    # duplicate some Gaussians so that equal (tile, depth) keys exist and the tie order matters
+    means = torch.cat([means, means[:500]]); quats = torch.cat([quats, quats[:500]]); scales = torch.cat([scales, scales[:500]])
+    m, q, s, v, k = _gpu((means, quats, scales, vm, Ks), cuda_dev)
+    radii, means2d, depths = fully_fused_projection(m, None, q, s, v, k, w, h)[:3]
+    tw, th = math.ceil(w / 16), math.ceil(h / 16)
+    t1, i1, f1 = isect_tiles(means2d, radii, depths, 16, tw, th)
+    o1 = isect_offset_encode(i1, views, tw, th)
+    t2, i2, f2, o2 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th)
+    assert torch.equal(t1, t2) and torch.equal(i1, i2) and torch.equal(f1, f2) and torch.equal(o1, o2)
+    r_t, r_i, r_f = O.isect_tiles(means2d.cpu(), radii.cpu(), depths.cpu(), 16, tw, th)
+    assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
+    assert int((i1[1:] == i1[:-1]).sum()) > 100, "the scene must contain equal keys"
+    assert int((o2.flatten()[1:] - o2.flatten()[:-1]).max()) > (600 if n >= 20000 else 50)
