@@ -141,16 +141,35 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
     pos[r] += s_bin_start[d] + s_cnt[warp][d];
     s_keys[pos[r]] = key[r];
   }
-  // ---- decoupled look-back (thread t <-> digit t): sum of the digit's counts over all earlier tiles
+  // ---- decoupled look-back (thread t <-> digit t): sum of the digit's counts over all earlier tiles.
+  //      Four predecessors are polled at once (independent loads in flight) and consumed in order, so a chain
+  //      of k aggregate-only predecessors costs ~k/4 memory round trips instead of k.
   u32 excl_prev = 0;
-  for (int p = tile - 1; p >= 0; --p) {
-    const u32* ps = const_cast<const u32*>(status) + (size_t)p * RADIX + t;
-    u32 sv;
-    do {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv) : "l"(ps) : "memory");
-    } while ((sv & LB_FLAGS) == 0u);
-    excl_prev += sv & LB_VALUE;
-    if ((sv & LB_FLAGS) == LB_PREFIX) break;
+  {
+    int p = tile - 1;
+    bool found = (tile == 0);
+    while (!found) {
+      u32 sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sv[i] = LB_PREFIX;  // before the first tile: an empty inclusive prefix
+        if (p - i >= 0) {
+          const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv[i]) : "l"(ps) : "memory");
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (found) break;
+        while ((sv[i] & LB_FLAGS) == 0u) {  // not published yet: poll this one
+          const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv[i]) : "l"(ps) : "memory");
+        }
+        excl_prev += sv[i] & LB_VALUE;
+        found = (sv[i] & LB_FLAGS) == LB_PREFIX;
+      }
+      p -= 4;
+    }
   }
   if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
   s_gbase[t] = (int)((gh_incl - gh) + excl_prev) - (int)(bin_incl - bcount);

@@ -249,14 +249,23 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
 
 @torch.no_grad()
 def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int,
-                            tile_height: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go, bit-identical to calling the two (tests
-    check it), through the tile-partitioned path of csrc/tilesort.cu: per-tile histogram -> offsets, atomic-slot
-    emission into tile segments, per-tile shared-memory sort.  Falls back to the radix path when a tile holds
-    more than ``rs_tile_sort_max_segment()`` intersections.  One device->host read (M and the longest segment).
-    -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32."""
+                            tile_height: int, method: str = "radix") -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go.
+    -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32.
+
+    ``method="radix"`` (default): emit + onesweep radix sort + offset encode.  ``method="tile"``: the
+    tile-partitioned path of csrc/tilesort.cu (per-tile histogram -> offsets, atomic-slot emission into tile
+    segments, per-tile shared-memory bitonic sort; falls back to radix when a tile holds more than
+    ``rs_tile_sort_max_segment()`` intersections).  Both are bit-identical (tests check it); on B200 at BASELINE
+    config 2 the tile path moves 5x fewer bytes but measured SLOWER (0.79 ms vs 0.61 ms: 6.9 M atomics in count
+    and emit cost 0.35 ms, the bitonic network 0.43 ms), so it is not the default -- see DESIGN.md."""
     if tile_size != TILE_SIZE:
         raise NotImplementedError("tile_size must be 16")
+    if method == "radix":
+        C = depths.shape[0]
+        tiles, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)
+        return tiles, ids, flat, isect_offset_encode(ids, C, tile_width, tile_height)
+    assert method == "tile", method
     lib = _be.load()
     C, N = depths.shape
     assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)

@@ -585,7 +585,7 @@ def test_tile_partitioned_isect_matches_radix_path(cuda_dev, views, w, h, n, boo
     tw, th = math.ceil(w / 16), math.ceil(h / 16)
     t1, i1, f1 = isect_tiles(means2d, radii, depths, 16, tw, th)
     o1 = isect_offset_encode(i1, views, tw, th)
-    t2, i2, f2, o2 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th)
+    t2, i2, f2, o2 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th, method="tile")
     assert torch.equal(t1, t2) and torch.equal(i1, i2) and torch.equal(f1, f2) and torch.equal(o1, o2)
     r_t, r_i, r_f = O.isect_tiles(means2d.cpu(), radii.cpu(), depths.cpu(), 16, tw, th)
     assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
