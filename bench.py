@@ -366,6 +366,8 @@ def main():
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         from datetime import timedelta
         dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))
