@@ -179,11 +179,11 @@ template <int DP, int BATCH> struct Smem {
 
 // gather one batch (ids already in s.ids[buf]) with 16-byte cp.async copies; consecutive threads copy
 // consecutive 16-byte chunks of one record, so each 64-byte record is one coalesced request
-template <int DP, int BATCH>
+template <int DP, int BATCH, int NT = RT>
 __device__ __forceinline__ void issue_gather(Smem<DP, BATCH>& s, int buf, int count, const RasterArgs& a, int t) {
   constexpr int CH = 4 + DP / 4;
   const int total = count * CH;
-  for (int i = t; i < total; i += RT) {
+  for (int i = t; i < total; i += NT) {
     const int slot = i / CH, ch = i - slot * CH;
     const int id = s.ids[buf][slot];
     if (ch < 4) {
@@ -368,6 +368,161 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
     a.out_normals[pix * 3] = nx; a.out_normals[pix * 3 + 1] = ny; a.out_normals[pix * 3 + 2] = nz;
     a.last_ids[pix] = last_id;
     a.median_ids[pix] = med_id;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward, 2 px/lane
+// Variant of the forward kernel in which a warp owns an 8x8 pixel block and every lane blends TWO pixels of the
+// same column, (x, y) and (x, y+4).  The Gaussian record loads, the loop control and the x-dependent part of
+// the quadratic form (dx, a'dx^2, b'dx) are shared by the two pixels, which cuts the per-pixel instruction
+// count of the (issue-bound) alpha test; 4 warps (128 threads) per tile, 128-Gaussian batches.
+constexpr int RT2 = 128;
+
+template <int DP, int BATCH>
+__global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tile_id = blockIdx.x;
+  const int tiles_per_cam = a.tile_w * a.tile_h;
+  const int cam = tile_id / tiles_per_cam;
+  const int tl = tile_id - cam * tiles_per_cam;
+  const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
+  const int start = __ldg(a.offsets + tile_id);
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
+  const int pxi = x0 + (lane & 7);
+  const int pyi[2] = {y0 + (lane >> 3), y0 + (lane >> 3) + 4};
+  const bool inside[2] = {pxi < a.W && pyi[0] < a.H, pxi < a.W && pyi[1] < a.H};
+  const float px = pxi + 0.5f;
+  const float py[2] = {pyi[0] + 0.5f, pyi[1] + 0.5f};
+  const float rcx = x0 + 4.0f, rcy = y0 + 4.0f;
+
+  float T[2] = {inside[0] ? 1.f : 0.f, inside[1] ? 1.f : 0.f}, T_out[2] = {1.f, 1.f};
+  float dsum[2] = {0.f, 0.f}, tmed[2] = {0.f, 0.f}, nx[2] = {0.f, 0.f}, ny[2] = {0.f, 0.f}, nz[2] = {0.f, 0.f};
+  float acc[2][DP];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < DP; ++k) acc[h][k] = 0.f;
+  int last_id[2] = {start - 1, start - 1}, med_id[2] = {-1, -1};
+
+  const int nb = (end - start + BATCH - 1) / BATCH;
+  if (nb > 0) {
+    for (int i = t; i < BATCH; i += RT2) { const int g = start + i; s.ids[0][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH, RT2>(s, 0, min(BATCH, end - start), a, t);
+    if (nb > 1)
+      for (int i = t; i < BATCH; i += RT2) { const int g = start + BATCH + i; s.ids[1][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+  }
+  bool warp_done = !__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f);
+  for (int b = 0; b < nb; ++b) {
+    rs::cp_async_wait_all();
+    if (__syncthreads_count(T[0] != 0.f || T[1] != 0.f) == 0) break;
+    int next_id[BATCH / RT2];
+    if (b + 1 < nb) {
+      issue_gather<DP, BATCH, RT2>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
+      if (b + 2 < nb) {
+#pragma unroll
+        for (int r = 0; r < BATCH / RT2; ++r) {
+          const int g = start + (b + 2) * BATCH + r * RT2 + t;
+          next_id[r] = g < end ? __ldg(a.flatten_ids + g) : 0;
+        }
+      }
+    }
+    if (!warp_done) {
+      const int buf = b & 1;
+      const int base_idx = start + b * BATCH;
+      const int bcount = min(BATCH, end - base_idx);
+      for (int g0 = 0; g0 < bcount; g0 += 32) {
+        const int j = g0 + lane;
+        bool hit = false;
+        if (j < bcount) {
+          const float4 f = s.q0[buf][j];
+          hit = fabsf(f.x - rcx) <= f.z + 3.5f && fabsf(f.y - rcy) <= f.w + 3.5f;
+        }
+        unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+        while (m) {
+          const int jj = g0 + __ffs(m) - 1;
+          m &= m - 1;
+          const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
+          const float dx = q0.x - px;
+          const float A = q1.x * dx * dx, B = q1.y * dx;   // shared by both pixels of the column
+          float dy[2], alpha[2];
+          bool ok[2];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            dy[h] = q0.y - py[h];
+            const float sig = fmaf(fmaf(q1.z, dy[h], B), dy[h], A);
+            alpha[h] = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
+            ok[h] = sig >= 0.f && alpha[h] >= RS_ALPHA_MIN;
+          }
+          if (ok[0] || ok[1]) {
+            const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+            const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+            const float tb = q2.x + q2.y * dx;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (ok[h]) {
+                const float nT = T[h] * (1.f - alpha[h]);
+                if (!(nT > RS_T_STOP)) {
+                  if (T[h] != 0.f) { T_out[h] = T[h]; T[h] = 0.f; }
+                } else {
+                  const float vis = alpha[h] * T[h];
+                  const float tt = tb + q2.z * dy[h];
+                  dsum[h] += vis * tt;
+                  nx[h] += vis * q3.x; ny[h] += vis * q3.y; nz[h] += vis * q3.z;
+#pragma unroll
+                  for (int k = 0; k < DP / 4; ++k) {
+                    const float4 cc = cp[k];
+                    acc[h][4 * k] += vis * cc.x; acc[h][4 * k + 1] += vis * cc.y;
+                    acc[h][4 * k + 2] += vis * cc.z; acc[h][4 * k + 3] += vis * cc.w;
+                  }
+#if RS_MEDIAN_INCLUSIVE
+                  if (T[h] > 0.5f && nT <= 0.5f) { tmed[h] = tt; med_id[h] = base_idx + jj; }
+#else
+                  if (T[h] > 0.5f && nT < 0.5f) { tmed[h] = tt; med_id[h] = base_idx + jj; }
+#endif
+                  last_id[h] = base_idx + jj;
+                  T[h] = nT;
+                }
+              }
+            }
+          }
+        }
+        if (!__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f)) { warp_done = true; break; }
+      }
+    }
+    if (b + 2 < nb) {
+#pragma unroll
+      for (int r = 0; r < BATCH / RT2; ++r) s.ids[b & 1][r * RT2 + t] = next_id[r];
+    }
+  }
+  rs::cp_async_wait_all();
+
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (!inside[h]) continue;
+    float Tf = T[h] == 0.f ? T_out[h] : T[h];
+    const size_t pix = ((size_t)cam * a.H + pyi[h]) * a.W + pxi;
+    const float il = inv_ray_len(a, cam, px, py[h]);
+    float* oc = a.out_colors + pix * a.D;
+    const float* bg = a.backgrounds ? a.backgrounds + (size_t)cam * a.D : nullptr;
+    const float ed_scale = 1.f / fmaxf(1.f - Tf, 1e-10f);
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+      if (k < a.D) {
+        float v = acc[h][k] + (bg ? Tf * __ldg(bg + k) : 0.f);
+        if (k == a.ed_channel) v *= ed_scale;
+        oc[k] = v;
+      }
+    a.out_alphas[pix] = 1.f - Tf;
+    a.out_T[pix] = Tf;
+    a.out_dexp[pix] = dsum[h] * il;
+    a.out_dmed[pix] = tmed[h] * il;
+    a.out_normals[pix * 3] = nx[h]; a.out_normals[pix * 3 + 1] = ny[h]; a.out_normals[pix * 3 + 2] = nz[h];
+    a.last_ids[pix] = last_id[h];
+    a.median_ids[pix] = med_id[h];
   }
 }
 
@@ -558,9 +713,17 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   rasterize_fwd_kernel<DP, B, STATS><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
+static int g_raster_variant = 0;  // 0: one pixel per lane (8x4 per warp); 1: two pixels per lane (8x8 per warp), DP == 4
+
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
     if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
+    if (g_raster_variant == 1) {
+      constexpr int B2 = 128;
+      const size_t smem = sizeof(Smem<DP, B2>);
+      rasterize_fwd2_kernel<DP, B2><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);
+      RS_RETURN_LAST_ERROR();
+    }
   }
   return launch_fwd2<DP, false>(a, st);
 }
@@ -596,6 +759,9 @@ bool check_common(const RasterArgs& a) {
 }  // namespace
 
 extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
+
+// tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
+extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
 
 // Work counters for the roofline arithmetic (bench.py): while `dev_counters` (4 x u64, device, zeroed by the caller)
 // is set, forward launches with <= 4 colour channels run an instrumented kernel that adds

@@ -118,6 +118,7 @@ int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the
 /* Work counters for roofline arithmetic: while set, forward launches with <= 4 channels run an instrumented
  * kernel adding {Q visited pairs, Qc blended pairs, warp evaluations, blending warp evaluations} (4 x u64). */
 void rs_raster_set_stats(unsigned long long* dev_counters);
+void rs_raster_set_variant(int variant); /* tuning knob: 0 = one pixel per lane (default), 1 = two pixels per lane */
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
                  const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,

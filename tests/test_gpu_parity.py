@@ -591,3 +591,37 @@ def test_tile_partitioned_isect_matches_radix_path(cuda_dev, views, w, h, n, boo
     assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
     assert int((i1[1:] == i1[:-1]).sum()) > 100, "the scene must contain equal keys"
     assert int((o2.flatten()[1:] - o2.flatten()[:-1]).max()) > (600 if n >= 20000 else 50)
+
+
+def test_forward_two_pixels_per_lane_variant(cuda_dev):
+    """The experimental forward variant (8x8 pixels per warp, two per lane; rs_raster_set_variant(1)) against the
+    oracle and against the default kernel, incl. multi-batch tiles, image edges and a background."""
+    from gsplat.cuda._wrapper import rasterize_to_pixels
+    from radegs_b200 import backend as be
+    lib = be.load()
+    for (n, w, h, views) in ((2500, 150, 90, 2), (9000, 64, 48, 1)):
+        cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views)
+        inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, 4)
+        bg = torch.rand(views, 4, generator=torch.Generator().manual_seed(3))
+        ref = O.rasterize_to_pixels(inp["means2d"], inp["conics"], inp["colors"], inp["opacities"], inp["ray_ts"],
+                                    inp["ray_planes"], inp["normals"], Ks, w, h, 16, offs, flat, backgrounds=bg,
+                                    return_aux=True)
+        d = {k: v.to(cuda_dev) for k, v in inp.items()}
+        outs = []
+        try:
+            for variant in (0, 1):
+                lib.rs_raster_set_variant(variant)
+                outs.append(rasterize_to_pixels(d["means2d"], d["conics"], d["colors"], d["opacities"], w, h, 16,
+                                                offs.to(cuda_dev), flat.to(cuda_dev), backgrounds=bg.to(cuda_dev),
+                                                ray_ts=d["ray_ts"], ray_planes=d["ray_planes"], normals=d["normals"],
+                                                Ks=Ks.to(cuda_dev), return_ids=True))
+        finally:
+            lib.rs_raster_set_variant(0)
+        keep = ~ref[5]["fragile"]
+        for i, nm in enumerate(["colors", "alphas", "expected_depths", "median_depths", "normals"]):
+            ok, msg = close_report(nm, outs[1][i], ref[i], mask=keep)
+            assert ok, msg
+            ok, msg = close_report(nm + " (variant 1 vs 0)", outs[1][i], outs[0][i], mask=keep)
+            assert ok, msg
+        assert bool(((outs[1][5].cpu() == ref[5]["last_ids"]) | ref[5]["fragile"]).all())
+        assert bool(((outs[1][6].cpu() == ref[5]["median_ids"]) | ref[5]["fragile"]).all())
