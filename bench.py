@@ -162,19 +162,76 @@ class Workload:
         loss.backward()
         return loss
 
+    # ---- end-to-end step: host inputs -> device every step, loss -> host every step, software-pipelined the way a
+    # training loop's data loader and logger are: the next step's inputs are copied on a side stream while the
+    # current step computes, and the loss lands in a pinned buffer that is read one step later.
+    def _e2e_init(self):
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.in_bufs = [dict(vm=torch.empty_like(self.viewmat), K=torch.empty_like(self.K), gt=torch.empty_like(self.gt),
+                             ev=torch.cuda.Event()) for _ in range(2)]
+        self.loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+        self.loss_ev = [None, None]
+        self.e2e_i = 0
+        self._prefetch(0)
+
+    def _prefetch(self, slot):
+        b = self.in_bufs[slot]
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))   # buffer reuse: previous consumer is done
+        with torch.cuda.stream(self.copy_stream):
+            b["vm"].copy_(self.viewmat_host, non_blocking=True)
+            b["K"].copy_(self.K_host, non_blocking=True)
+            b["gt"].copy_(self.gt_host, non_blocking=True)
+            b["ev"].record(self.copy_stream)
+
     def step_e2e(self):
+        if not hasattr(self, "copy_stream"):
+            self._e2e_init()
+        i = self.e2e_i
+        self.e2e_i += 1
+        b = self.in_bufs[i & 1]
+        torch.cuda.current_stream(self.device).wait_event(b["ev"])
+        self._prefetch((i + 1) & 1)                      # next step's H2D overlaps this step's kernels
         self.zero_grad()
-        vm = self.viewmat_host.to(self.device, non_blocking=True)
-        K = self.K_host.to(self.device, non_blocking=True)
-        gt = self.gt_host.to(self.device, non_blocking=True)
-        loss = self.forward_loss(vm, K, gt)
+        loss = self.forward_loss(b["vm"], b["K"], b["gt"])
         loss.backward()
         return loss
 
+    def read_loss_async(self, loss):
+        """Queue the D2H copy of this step's loss; return the previous step's value (already on the host)."""
+        i = self.e2e_i - 1
+        self.loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.loss_ev[i & 1] = ev
+        prev = self.loss_ev[(i + 1) & 1]
+        if prev is None:
+            return None
+        prev.synchronize()
+        return float(self.loss_host[(i + 1) & 1][0])
+
+    # ---- multi-GPU: Gaussian-gradient all-reduce.  The SH coefficients are 192 of the 236 B per Gaussian and their
+    # gradient is final as soon as the colour backward has run, so its all-reduce is launched from a gradient hook
+    # (async, NCCL stream) and overlaps the projection backward; the remaining small gradients go in one flat bucket.
+    def enable_overlapped_allreduce(self):
+        import torch.distributed as dist
+        self.pending = []
+        self.collectives_on = True
+        big = self.params["sh_coeffs"]
+
+        def hook(param):
+            if self.collectives_on:          # switched off for the rank-0-only per-kernel timing steps
+                self.pending.append(dist.all_reduce(param.grad, async_op=True))
+        big.register_post_accumulate_grad_hook(hook)
+
     def allreduce_grads(self):
         import torch.distributed as dist
-        flat = torch.cat([v.grad.reshape(-1) for v in self.params.values()])
+        small = [v.grad.reshape(-1) for k, v in self.params.items() if k != "sh_coeffs" or not hasattr(self, "pending")]
+        flat = torch.cat(small)
         dist.all_reduce(flat)
+        if hasattr(self, "pending"):
+            for w in self.pending:
+                w.wait()
+            self.pending.clear()
         return flat
 
 
@@ -377,6 +434,8 @@ def main():
 
     wl = Workload(args.config, device, rank, world)
     wl.fused_loss = not args.torch_loss
+    if world > 1:
+        wl.enable_overlapped_allreduce()
 
     def resident():
         wl.step_resident()
@@ -387,7 +446,7 @@ def main():
         loss = wl.step_e2e()
         if world > 1:
             wl.allreduce_grads()
-        return float(loss.item())   # device -> host read of the step's result
+        return wl.read_loss_async(loss)   # device -> host read of the result, every step, one step deferred
 
     for _ in range(warmup):
         resident()
@@ -419,7 +478,8 @@ def main():
                    "views_per_step": world, "parallelism": f"camera-sharded x{world}, Gaussians replicated"
                                                              + (", NCCL allreduce of parameter grads" if world > 1 else ""),
                    "l2": "inputs exceed L2 (236 MB of SH coefficients + per-step intersection buffers > 126 MB)",
-                   "optimizer": "none (hot path only)", "n_isects": int(wl.last_meta["flatten_ids"].numel())},
+                   "optimizer": "none (hot path only)",
+                   "e2e_pipeline": "next step's H2D on a copy stream; loss D2H read one step later (pinned)", "n_isects": int(wl.last_meta["flatten_ids"].numel())},
         "clocks": clocks.summary(),
         "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
                 "ms_per_step": ms_e2e / args.steps},
@@ -430,8 +490,9 @@ def main():
         # brackets every entry point with CUDA events on the launching stream
         lib.rs_timing_enable(1)
         n_t = 5
+        wl.collectives_on = False       # rank 0 only from here on: NO collective may be issued
         for _ in range(n_t):
-            wl.step_resident()          # rank 0 only: NO collective in here
+            wl.step_resident()
         torch.cuda.synchronize(device)
         spans = backend.timing_collect()
         lib.rs_timing_enable(0)
