@@ -427,7 +427,19 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         from datetime import timedelta
-        dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))
+        # NCCL prints its version banner on fd 1 when the communicator is created: point fd 1 at stderr until the
+        # first collective has run, so that stdout carries nothing but the JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device, timeout=timedelta(seconds=180))
+            dist.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from radegs_b200 import backend
     lib = backend.load()
     warmup = max(args.warmup, 3)
