@@ -78,13 +78,19 @@ pack_colors_kernel(const float* __restrict__ colors, long long rows, int D, int 
   out[i] = k < D ? __ldg(colors + r * D + k) : 0.f;
 }
 
-// gradient record layout (16 floats per (camera, Gaussian)):
-//   0 gx  1 gy | 2 ga 3 gb 4 gc (raw conic) | 5 go | 6 g_ray_t 7 g_rpx 8 g_rpy | 9 gnx 10 gny 11 gnz |
-//   12..15 colour channels 0..3 (only when the colours are padded to 4 channels, i.e. DP == 4)
+// gradient record layout (16 floats per (camera, Gaussian)), S = sum over the pixels the Gaussian was blended into:
+//   0 S v_sigma*dx  1 S v_sigma*dy | 2 ga 3 gb 4 gc (raw conic) | 5 S v_sigma | 6 g_ray_t 7 g_rpx 8 g_rpy |
+//   9 gnx 10 gny 11 gnz | 12..15 colour channels 0..3 (only when the colours are padded to 4 channels, DP == 4)
+// The compositing kernels leave the two per-Gaussian linear maps to this kernel (they only need per-Gaussian
+// constants, which are in the geometry record):
+//   v_means2d = (a*S0 + b*S1 + rpx*g_ray_t, b*S0 + c*S1 + rpy*g_ray_t)   (d sigma/d(dx,dy) with the raw conic + the
+//                                                                          ray-plane term of t = ray_t + rp.d)
+//   v_opacity = -S5 / o                                                   (alpha = o e^-sigma: v_o = -v_sigma / o)
 // thread per Gaussian, looping over cameras, so the opacity gradient (shared by all cameras when the input
 // opacity is [N]) is summed in a register.
 __global__ void __launch_bounds__(256)
-unpack_geom_grad_kernel(const float4* __restrict__ gg, const float2* __restrict__ abs_grad, int C, int N,
+unpack_geom_grad_kernel(const float4* __restrict__ gg, const float4* __restrict__ geom,
+                        const float2* __restrict__ abs_grad, int C, int N,
                         const float* __restrict__ opacities, int opac_per_cam,
                         const float* __restrict__ compensations, float2* __restrict__ v_means2d,
                         float2* __restrict__ v_means2d_abs, float* __restrict__ v_conics,
@@ -97,10 +103,12 @@ unpack_geom_grad_kernel(const float4* __restrict__ gg, const float2* __restrict_
   for (int c = 0; c < C; ++c) {
     const long long e = (long long)c * N + n;
     const float4 g0 = gg[e * 4], g1 = gg[e * 4 + 1], g2 = gg[e * 4 + 2], g3 = gg[e * 4 + 3];
-    v_means2d[e] = make_float2(g0.x, g0.y);
+    const float4 q1 = __ldg(geom + e * 4 + 1), q2 = __ldg(geom + e * 4 + 2);
+    const float ca = 2.f * RS_LN2 * q1.x, cb = RS_LN2 * q1.y, cc = 2.f * RS_LN2 * q1.z;  // raw conic
+    v_means2d[e] = make_float2(ca * g0.x + cb * g0.y + q2.y * g1.z, cb * g0.x + cc * g0.y + q2.z * g1.z);
     if (v_means2d_abs) v_means2d_abs[e] = abs_grad[e];
     v_conics[e * 3] = g0.z; v_conics[e * 3 + 1] = g0.w; v_conics[e * 3 + 2] = g1.x;
-    float go = g1.y;
+    float go = q1.w > 0.f ? -g1.y / q1.w : 0.f;
     if (compensations) {
       const float comp = __ldg(compensations + e);
       v_compensations[e] = go * __ldg(opacities + (opac_per_cam ? e : n));
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
     for (int k = 0; k < DP; ++k)
       if (k < a.D) {
         float v = acc[k] + (bg ? T * __ldg(bg + k) : 0.f);
-        if (k == a.ed_channel) v *= ed_scale;  // expected depth: accumulated depth / alpha
+        v *= (k == a.ed_channel) ? ed_scale : 1.f;  // expected depth: accumulated depth / alpha
         oc[k] = v;
       }
     a.out_alphas[pix] = 1.f - T;
@@ -369,6 +377,13 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
     a.last_ids[pix] = last_id;
     a.median_ids[pix] = med_id;
   }
+}
+
+// sigma' of the two-pixels-per-lane kernels: the x-dependent terms (adx2 = a'dx^2, bdx = b'dx) are shared by the
+// two pixels of a column.  Every operation is individually rounded / explicitly fused, so the forward and the
+// backward kernel take the same alpha >= 1/255 decisions.
+__device__ __forceinline__ float sigma_col(float adx2, float bdx, float c, float dy) {
+  return fmaf(fmaf(c, dy, bdx), dy, adx2);
 }
 
 // ------------------------------------------------------------------------------------------------ forward, 2 px/lane
@@ -447,13 +462,13 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
           m &= m - 1;
           const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
           const float dx = q0.x - px;
-          const float A = q1.x * dx * dx, B = q1.y * dx;   // shared by both pixels of the column
+          const float A = __fmul_rn(__fmul_rn(q1.x, dx), dx), B = __fmul_rn(q1.y, dx);   // shared by both pixels of the column
           float dy[2], alpha[2];
           bool ok[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             dy[h] = q0.y - py[h];
-            const float sig = fmaf(fmaf(q1.z, dy[h], B), dy[h], A);
+            const float sig = sigma_col(A, B, q1.z, dy[h]);
             alpha[h] = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
             ok[h] = sig >= 0.f && alpha[h] >= RS_ALPHA_MIN;
           }
@@ -513,7 +528,7 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
     for (int k = 0; k < DP; ++k)
       if (k < a.D) {
         float v = acc[h][k] + (bg ? Tf * __ldg(bg + k) : 0.f);
-        if (k == a.ed_channel) v *= ed_scale;
+        v *= (k == a.ed_channel) ? ed_scale : 1.f;
         oc[k] = v;
       }
     a.out_alphas[pix] = 1.f - Tf;
@@ -545,6 +560,19 @@ __device__ __forceinline__ void commit_color_grads(const float (&v_c)[DP], float
   }
 }
 
+// The median depth of a pixel is the ray distance t = ray_t + ray_plane . d of ONE Gaussian (median_ids): its
+// gradient is three scalar atomics per pixel, issued once here instead of a compare + select per blended pair in
+// the compositing loop.
+__device__ __forceinline__ void commit_median_grad(const RasterArgs& a, int med_id, float v_dmed, float px, float py) {
+  if (med_id < 0 || v_dmed == 0.f) return;
+  const int gid = __ldg(a.flatten_ids + med_id);
+  const float4 q0 = __ldg(a.geom + (size_t)gid * 4);
+  float* rec = a.geom_grad + (size_t)gid * 16;
+  atomicAdd(rec + 6, v_dmed);
+  atomicAdd(rec + 7, v_dmed * (q0.x - px));
+  atomicAdd(rec + 8, v_dmed * (q0.y - py));
+}
+
 template <int DP, int BATCH, bool ABSGRAD>
 __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -562,24 +590,22 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
   const float T_final = inside ? a.out_T[pix] : 1.f;
   // "ED" channel: out = S / max(alpha, 1e-10)  ->  v_S = v_out / max(alpha,..),  v_alpha += -out * v_out / alpha
   float v_alpha_ed = 0.f;
-  if (a.ed_channel >= 0 && inside) {
+  if (a.ed_channel >= 0 && inside) {   // select form: a dynamic index would push v_c into local memory
     const float alpha_out = 1.f - T_final;
     const float sc = 1.f / fmaxf(alpha_out, 1e-10f);
+    const float oc = __ldg(a.out_colors + pix * a.D + a.ed_channel);
+    const float vce = __ldg(a.v_colors + pix * a.D + a.ed_channel);   // re-read: v_c[ed_channel] would be a dynamic index
+    if (alpha_out > 1e-10f) v_alpha_ed = -oc * vce * sc;
 #pragma unroll
-    for (int k = 0; k < DP; ++k)
-      if (k == a.ed_channel) {
-        if (alpha_out > 1e-10f) v_alpha_ed = -__ldg(a.out_colors + pix * a.D + k) * v_c[k] * sc;
-        v_c[k] *= sc;
-      }
+    for (int k = 0; k < DP; ++k) v_c[k] *= (k == a.ed_channel) ? sc : 1.f;
   }
   const int last_id = inside ? a.last_ids[pix] : start - 1;
-  const int med_id = inside ? a.median_ids[pix] : -1;
   const float il = inside ? inv_ray_len(a, c.cam, px, py) : 0.f;
 #if RS_NORMALIZE_EXPECTED_DEPTH
 #error "alpha-normalised expected depth (Q1) needs the extra dDexp/dalpha term in the backward"
 #endif
   const float v_dsum = inside ? __ldg(a.v_dexp + pix) * il : 0.f;
-  const float v_dmed = inside ? __ldg(a.v_dmed + pix) * il : 0.f;
+  if (inside) commit_median_grad(a, a.median_ids[pix], __ldg(a.v_dmed + pix) * il, px, py);
   const float v_n0 = inside ? __ldg(a.v_normals + pix * 3) : 0.f;
   const float v_n1 = inside ? __ldg(a.v_normals + pix * 3 + 1) : 0.f;
   const float v_n2 = inside ? __ldg(a.v_normals + pix * 3 + 2) : 0.f;
@@ -661,18 +687,14 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         }
         const float v_alpha = T * w - R * ra + tfin_term * ra;
         R += vis * w;
-        const float v_t = vis * v_dsum + ((valid && idx == med_id) ? v_dmed : 0.f);
+        const float v_t = vis * v_dsum;   // (the median Gaussian's extra term: commit_median_grad)
         const bool unclamped = valid && oe <= RS_ALPHA_MAX;
         const float v_sig = unclamped ? -am * v_alpha : 0.f;
-        const float v_o = unclamped ? ex * v_alpha : 0.f;
-        // d sigma / d(dx,dy) with the raw conic (a,b,c) = ln2 * (2 q1.x, q1.y, 2 q1.z)
-        const float vs2 = v_sig * RS_LN2;
-        const float gx = vs2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y;
-        const float gy = vs2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z;
-        const float hx = 0.5f * dx * v_sig, hy = 0.5f * dy * v_sig;
+        // the record carries the moments S v_sigma*(dx, dy, 1); unpack_geom_grad_kernel turns them into the
+        // means2d / opacity gradients (per-Gaussian linear maps)
         float gq[16];
-        gq[0] = gx; gq[1] = gy;
-        gq[2] = hx * dx; gq[3] = 2.f * hx * dy; gq[4] = hy * dy; gq[5] = v_o;
+        gq[0] = v_sig * dx; gq[1] = v_sig * dy;
+        gq[2] = 0.5f * dx * gq[0]; gq[3] = dy * gq[0]; gq[4] = 0.5f * dy * gq[1]; gq[5] = v_sig;
         gq[6] = v_t; gq[7] = v_t * dx; gq[8] = v_t * dy;
         gq[9] = vis * v_n0; gq[10] = vis * v_n1; gq[11] = vis * v_n2;
         if constexpr (DP == 4) {
@@ -680,7 +702,12 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         } else {
           gq[12] = gq[13] = gq[14] = gq[15] = 0.f;
         }
-        const float ax = fabsf(gx), ay = fabsf(gy);
+        float ax = 0.f, ay = 0.f;
+        if constexpr (ABSGRAD) {   // |d L / d means2d| summed per pixel: needs the per-pixel gradient itself
+          const float vs2 = v_sig * RS_LN2;
+          ax = fabsf(vs2 * (2.f * q1.x * dx + q1.y * dy) + v_t * q2.y);
+          ay = fabsf(vs2 * (q1.y * dx + 2.f * q1.z * dy) + v_t * q2.z);
+        }
         const int id = __float_as_int(q2.w);  // flatten id carried by the record (s.ids is recycled concurrently)
         rs::warp_reduce_scatter<16>(gq, lane);
         {
@@ -703,6 +730,230 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
   rs::cp_async_wait_all();
 }
 
+// ------------------------------------------------------------------------------------------------ backward, 2 px/lane
+// Backward counterpart of rasterize_fwd2_kernel (<= 4 colour channels): a warp owns an 8x8 pixel block, every
+// lane differentiates the two pixels (x, y) and (x, y+4).  The two pixels share the Gaussian record loads, the
+// x-dependent terms and -- the point of the variant -- ONE 16-value warp reduction and ONE 64-byte RED per
+// (warp, Gaussian): their contributions are summed in registers first.  Because dx is common to the two pixels
+// the record's moments factor as dx * (sum over the two pixels), which removes most per-pixel multiplies.
+template <int BATCH, bool ABSGRAD>
+__global__ void __launch_bounds__(RT2, 4) rasterize_bwd2_kernel(const RasterArgs a) {
+  constexpr int DP = 4;
+  static_assert(BATCH == RT2, "one id per thread");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int tile_id = blockIdx.x;
+  const int tiles_per_cam = a.tile_w * a.tile_h;
+  const int cam = tile_id / tiles_per_cam;
+  const int tl = tile_id - cam * tiles_per_cam;
+  const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
+  const int start = __ldg(a.offsets + tile_id);
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
+  const int pxi = x0 + (lane & 7);
+  const float px = pxi + 0.5f;
+  const float rcx = x0 + 4.0f, rcy = y0 + 4.0f;
+
+  float py[2], v_c[2][4], v_ds[2], v_n[2][3], tfin[2], T[2], R[2];
+  int last_id[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pyi = y0 + (lane >> 3) + 4 * h;
+    const bool inside = pxi < a.W && pyi < a.H;
+    const size_t pix = inside ? ((size_t)cam * a.H + pyi) * a.W + pxi : 0;
+    py[h] = pyi + 0.5f;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) v_c[h][k] = (inside && k < a.D) ? __ldg(a.v_colors + pix * a.D + k) : 0.f;
+    const float T_final = inside ? a.out_T[pix] : 1.f;
+    float v_alpha_ed = 0.f;
+    if (a.ed_channel >= 0 && inside) {   // select form: a dynamic index would push v_c into local memory
+      const float alpha_out = 1.f - T_final;
+      const float sc = 1.f / fmaxf(alpha_out, 1e-10f);
+      const float oc = __ldg(a.out_colors + pix * a.D + a.ed_channel);
+      const float vce = __ldg(a.v_colors + pix * a.D + a.ed_channel);   // re-read: v_c[ed_channel] would be a dynamic index
+      if (alpha_out > 1e-10f) v_alpha_ed = -oc * vce * sc;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) v_c[h][k] *= (k == a.ed_channel) ? sc : 1.f;
+    }
+    last_id[h] = inside ? a.last_ids[pix] : start - 1;   // an outside pixel owns no list entry: never "valid"
+    const float il = inside ? inv_ray_len(a, cam, px, py[h]) : 0.f;
+    v_ds[h] = inside ? __ldg(a.v_dexp + pix) * il : 0.f;
+    if (inside) commit_median_grad(a, a.median_ids[pix], __ldg(a.v_dmed + pix) * il, px, py[h]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v_n[h][k] = inside ? __ldg(a.v_normals + pix * 3 + k) : 0.f;
+    float bgdot = 0.f;
+    if (a.backgrounds) {
+#pragma unroll
+      for (int k = 0; k < DP; ++k)
+        if (k < a.D) bgdot += __ldg(a.backgrounds + (size_t)cam * a.D + k) * v_c[h][k];
+    }
+    tfin[h] = inside ? T_final * (__ldg(a.v_alphas + pix) + v_alpha_ed - bgdot) : 0.f;
+    T[h] = T_final;
+    R[h] = 0.f;
+  }
+
+  // Select-free reduction of the eight "visibility x per-pixel constant" sums (normals 3, colours 4, ray_t): lane L
+  // keeps them in registers permuted by xa(L) = lane bits (4,3,2), i.e. register r holds slot r ^ xa, so that at
+  // every recursive-halving step "send the upper half of the registers, keep the lower half" is right for every
+  // lane.  The permutation is applied once, here, to the per-pixel constants.
+  const int xa = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  float ca[2][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float src[8] = {v_n[h][0], v_n[h][1], v_n[h][2], v_c[h][0], v_c[h][1], v_c[h][2], v_c[h][3], v_ds[h]};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ca[h][r] = src[r];
+#pragma unroll
+    for (int bit = 4; bit >= 1; bit >>= 1) {   // r -> r ^ xa as three conditional swaps
+      const bool sw = (xa & bit) != 0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if ((r & bit) == 0) {
+          const float lo = ca[h][r], up = ca[h][r | bit];
+          ca[h][r] = sw ? up : lo;
+          ca[h][r | bit] = sw ? lo : up;
+        }
+    }
+  }
+  // record slot this lane commits: lanes with bit 1 clear end up with slot xa of group A (gn 9..11, colours 12..15,
+  // g_ray_t 6), the others with slot xa of group B (S10 0, S01 1, ga 2, gc 4, g_rpx 7, g_rpy 8, S00 5, gb 3)
+  const int rec_slot = (int)(((lane & 2) ? 0x35874210u : 0x6FEDCBA9u) >> (4 * xa)) & 15;
+
+  int warp_last = max(last_id[0], last_id[1]);
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(RS_FULL_MASK, warp_last, d));
+  if (lane == 0) s.red[warp] = warp_last;
+  __syncthreads();
+  int blk_last = start - 1;
+#pragma unroll
+  for (int w = 0; w < RT2 / 32; ++w) blk_last = max(blk_last, s.red[w]);
+  const int nb = blk_last >= start ? (blk_last - start) / BATCH + 1 : 0;
+
+  if (nb > 0) {
+    const int bl = nb - 1;
+    { const int i = start + bl * BATCH + t; s.ids[bl & 1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH, RT2>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
+    if (bl >= 1) s.ids[(bl - 1) & 1][t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + t);
+  }
+  for (int b = nb - 1; b >= 0; --b) {
+    rs::cp_async_wait_all();
+    __syncthreads();
+    int next_id = 0;
+    if (b >= 1) {
+      issue_gather<DP, BATCH, RT2>(s, (b - 1) & 1, BATCH, a, t);
+      if (b >= 2) next_id = __ldg(a.flatten_ids + start + (b - 2) * BATCH + t);
+    }
+    const int buf = b & 1;
+    const int base_idx = start + b * BATCH;
+    const int hi = min(min(BATCH, end - base_idx) - 1, warp_last - base_idx);
+    for (int g0 = hi >= 0 ? (hi & ~31) : -32; g0 >= 0; g0 -= 32) {
+      const int j = g0 + lane;
+      bool hit = false;
+      if (j <= hi) {
+        const float4 f = s.q0[buf][j];
+        hit = fabsf(f.x - rcx) <= f.z + 3.5f && fabsf(f.y - rcy) <= f.w + 3.5f;
+      }
+      unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+      while (m) {
+        const int bit = 31 - __clz(m);   // back to front
+        m &= ~(1u << bit);
+        const int jj = g0 + bit;
+        const int idx = base_idx + jj;
+        const float2 xy = *reinterpret_cast<const float2*>(&s.q0[buf][jj]);
+        const float4 q1 = s.q1[buf][jj];
+        const float dx = xy.x - px;
+        const float adx2 = __fmul_rn(__fmul_rn(q1.x, dx), dx), bdx = __fmul_rn(q1.y, dx);
+        float dy[2], am[2];
+        bool valid[2], unc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          dy[h] = xy.y - py[h];
+          const float sig = sigma_col(adx2, bdx, q1.z, dy[h]);
+          const float oe = q1.w * rs::fast_exp2(-sig);
+          const float alpha = fminf(RS_ALPHA_MAX, oe);
+          valid[h] = idx <= last_id[h] && sig >= 0.f && alpha >= RS_ALPHA_MIN;
+          am[h] = valid[h] ? alpha : 0.f;   // an invalid pair acts as alpha = 0: every term below is an exact 0
+          unc[h] = valid[h] && oe <= RS_ALPHA_MAX;
+        }
+        if (!__any_sync(RS_FULL_MASK, valid[0] || valid[1])) continue;
+        const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+        const float4 cc = *reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+        const float tb = fmaf(q2.y, dx, q2.x);
+        float vis[2], v_t[2], v_sig[2], vsy[2], ax = 0.f, ay = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float ra = rs::fast_rcp(1.f - am[h]);
+          T[h] *= ra;   // transmittance in front of this Gaussian
+          vis[h] = am[h] * T[h];
+          const float tt = fmaf(q2.z, dy[h], tb);
+          float w = v_ds[h] * tt;
+          w = fmaf(v_n[h][0], q3.x, w); w = fmaf(v_n[h][1], q3.y, w); w = fmaf(v_n[h][2], q3.z, w);
+          w = fmaf(v_c[h][0], cc.x, w); w = fmaf(v_c[h][1], cc.y, w);
+          w = fmaf(v_c[h][2], cc.z, w); w = fmaf(v_c[h][3], cc.w, w);
+          const float v_alpha = fmaf(T[h], w, ra * (tfin[h] - R[h]));
+          R[h] = fmaf(vis[h], w, R[h]);
+          v_t[h] = vis[h] * v_ds[h];   // (the median Gaussian's extra term: commit_median_grad)
+          v_sig[h] = unc[h] ? -am[h] * v_alpha : 0.f;
+          vsy[h] = v_sig[h] * dy[h];
+          if constexpr (ABSGRAD) {
+            const float vs2 = v_sig[h] * RS_LN2;
+            ax += fabsf(vs2 * (2.f * q1.x * dx + q1.y * dy[h]) + v_t[h] * q2.y);
+            ay += fabsf(vs2 * (q1.y * dx + 2.f * q1.z * dy[h]) + v_t[h] * q2.z);
+          }
+        }
+        // the two pixels share dx: the record's moments are dx * (sums over the pair)
+        const float s0 = v_sig[0] + v_sig[1], sy = vsy[0] + vsy[1], t0 = v_t[0] + v_t[1];
+        float ga[8], gb[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ga[r] = fmaf(vis[1], ca[1][r], vis[0] * ca[0][r]);
+        gb[0] = dx * s0; gb[1] = sy; gb[2] = 0.5f * dx * gb[0]; gb[3] = 0.5f * fmaf(vsy[1], dy[1], vsy[0] * dy[0]);
+        gb[4] = dx * t0; gb[5] = fmaf(v_t[1], dy[1], v_t[0] * dy[0]); gb[6] = s0; gb[7] = dx * sy;
+        float* const rec = a.geom_grad + (size_t)__float_as_int(q2.w) * 16;
+        // A: 7 shuffles, no selects
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ga[r] += __shfl_xor_sync(RS_FULL_MASK, ga[r + 4], 16);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) ga[r] += __shfl_xor_sync(RS_FULL_MASK, ga[r + 2], 8);
+        ga[0] += __shfl_xor_sync(RS_FULL_MASK, ga[1], 4);
+        // B: recursive halving with selects, down to the 4-lane classes
+        {
+          int dist = 16;
+#pragma unroll
+          for (int half = 4; half >= 1; half /= 2) {
+            const bool upper = (lane & dist) != 0;
+#pragma unroll
+            for (int r = 0; r < half; ++r) {
+              const float send = upper ? gb[r] : gb[r + half];
+              const float keep = upper ? gb[r + half] : gb[r];
+              gb[r] = keep + __shfl_xor_sync(RS_FULL_MASK, send, dist);
+            }
+            dist >>= 1;
+          }
+        }
+        // lanes with bit 1 clear take the A slot, the others the B slot; then add the two halves
+        {
+          const bool upper = (lane & 2) != 0;
+          const float send = upper ? ga[0] : gb[0];
+          float keep = upper ? gb[0] : ga[0];
+          keep += __shfl_xor_sync(RS_FULL_MASK, send, 2);
+          keep += __shfl_xor_sync(RS_FULL_MASK, keep, 1);
+          if ((lane & 1) == 0) atomicAdd(rec + rec_slot, keep);
+        }
+        const int id = __float_as_int(q2.w);
+        if constexpr (ABSGRAD) {
+          float ab[2] = {ax, ay};
+          rs::warp_reduce_scatter<2>(ab, lane);
+          if ((lane & 15) == 0) atomicAdd(a.abs_grad + (size_t)id * 2 + (lane >> 4), ab[0]);
+        }
+      }
+    }
+    if (b >= 2) s.ids[b & 1][t] = next_id;
+  }
+  rs::cp_async_wait_all();
+}
+
 // ------------------------------------------------------------------------------------------------ launch
 template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
@@ -713,7 +964,7 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   rasterize_fwd_kernel<DP, B, STATS><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
-static int g_raster_variant = 0;  // 0: one pixel per lane (8x4 per warp); 1: two pixels per lane (8x8 per warp), DP == 4
+static int g_raster_variant = 1;  // DP == 4 only.  0: one pixel per lane (8x4 per warp); 1 (default): two pixels per lane (8x8 per warp)
 
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
@@ -739,6 +990,16 @@ template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_
   RS_RETURN_LAST_ERROR();
 }
 template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
+  if constexpr (DP == 4) {
+    if (g_raster_variant == 1) {   // must match the forward variant: the two share sigma_col()'s rounding
+      constexpr int B2 = RT2;
+      const size_t smem = sizeof(Smem<DP, B2>);
+      const int grid = a.C * a.tile_w * a.tile_h;
+      if (a.abs_grad) rasterize_bwd2_kernel<B2, true><<<grid, RT2, smem, st>>>(a);
+      else rasterize_bwd2_kernel<B2, false><<<grid, RT2, smem, st>>>(a);
+      RS_RETURN_LAST_ERROR();
+    }
+  }
   return a.abs_grad ? launch_bwd2<DP, true>(a, st) : launch_bwd2<DP, false>(a, st);
 }
 
@@ -762,6 +1023,7 @@ extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 
 // tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
 extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
+extern "C" int rs_raster_get_variant(void) { return g_raster_variant; }
 
 // Work counters for the roofline arithmetic (bench.py): while `dev_counters` (4 x u64, device, zeroed by the caller)
 // is set, forward launches with <= 4 colour channels run an instrumented kernel that adds
@@ -791,7 +1053,7 @@ extern "C" int rs_pack_colors(const float* colors, long long rows, int D, int DP
   RS_RETURN_LAST_ERROR();
 }
 
-extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad, int C, int N,
+extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* geom, const float* abs_grad, int C, int N,
                                    const float* opacities, int opac_per_cam, const float* compensations,
                                    float* v_means2d, float* v_means2d_abs, float* v_conics, float* v_opacities,
                                    float* v_compensations, float* v_ray_ts, float* v_ray_planes, float* v_normals,
@@ -799,13 +1061,13 @@ extern "C" int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad
   RsSpan span__("rs_unpack_geom_grad", stream);
   if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
   if ((long long)C * N == 0) return RS_OK;
-  if (!geom_grad || !v_means2d || !v_conics || !v_opacities || !v_ray_ts || !v_ray_planes || !v_normals)
+  if (!geom_grad || !geom || !v_means2d || !v_conics || !v_opacities || !v_ray_ts || !v_ray_planes || !v_normals)
     return RS_ERR_BAD_ARG;
   if (v_means2d_abs && !abs_grad) return RS_ERR_BAD_ARG;
   if (compensations && (!opacities || !v_compensations)) return RS_ERR_BAD_ARG;
   if (v_colors4 && (D < 1 || D > 4)) return RS_ERR_BAD_ARG;
   unpack_geom_grad_kernel<<<rs_div_up(N, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)geom_grad, (const float2*)abs_grad, C, N, opacities, opac_per_cam, compensations,
+      (const float4*)geom_grad, (const float4*)geom, (const float2*)abs_grad, C, N, opacities, opac_per_cam, compensations,
       (float2*)v_means2d, (float2*)v_means2d_abs, v_conics, v_opacities, v_compensations, v_ray_ts,
       (float2*)v_ray_planes, v_normals, v_colors4, color_per_cam, D);
   RS_RETURN_LAST_ERROR();

@@ -451,7 +451,7 @@ class _RasterizeToPixels(torch.autograd.Function):
                 _be.ptr(v_alphas), _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad),
                 _be.ptr(color_grad), _be.ptr(abs_grad), st), "rs_rasterize_bwd")
             _be.check(lib.rs_unpack_geom_grad(
-                _be.ptr(geom_grad), _be.ptr(abs_grad), C, N, _be.ptr(opacities), int(opac_per_cam),
+                _be.ptr(geom_grad), _be.ptr(geom), _be.ptr(abs_grad), C, N, _be.ptr(opacities), int(opac_per_cam),
                 _be.ptr(compensations), _be.ptr(v_means2d), _be.ptr(v_abs), _be.ptr(v_conics), _be.ptr(v_opac),
                 _be.ptr(v_comps), _be.ptr(v_ray_ts), _be.ptr(v_ray_planes), _be.ptr(v_nrm),
                 _be.ptr(v_col) if DP == 4 else None, int(color_per_cam), D, st), "rs_unpack_geom_grad")

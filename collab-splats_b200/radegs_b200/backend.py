@@ -49,12 +49,13 @@ _SIGNATURES = {
     "rs_raster_padded_channels": (_i, [_i]),
     "rs_raster_set_stats": (None, [_p]),
     "rs_raster_set_variant": (None, [_i]),
+    "rs_raster_get_variant": (_i, []),
     "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rs_pack_colors": (_i, [_p, _ll, _i, _i, _p, _p]),
     "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_p]),
     "rs_rasterize_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 4 + [_p] * 5
                          + [_p, _p, _p] + [_p]),
-    "rs_unpack_geom_grad": (_i, [_p, _p, _i, _i, _p, _i, _p] + [_p] * 9 + [_i, _i, _p]),
+    "rs_unpack_geom_grad": (_i, [_p, _p, _p, _i, _i, _p, _i, _p] + [_p] * 9 + [_i, _i, _p]),
     "rs_sh_colors_fwd": (_i, [_i, _i, _i, _i] + [_p] * 6 + [_p]),
     "rs_sh_colors_bwd": (_i, [_i, _i, _i, _i] + [_p] * 5 + [_i] + [_p] * 3 + [_p]),
     "rs_unpack_colors_grad": (_i, [_p, _ll, _i, _i, _p, _p]),

@@ -118,7 +118,10 @@ int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the
 /* Work counters for roofline arithmetic: while set, forward launches with <= 4 channels run an instrumented
  * kernel adding {Q visited pairs, Qc blended pairs, warp evaluations, blending warp evaluations} (4 x u64). */
 void rs_raster_set_stats(unsigned long long* dev_counters);
-void rs_raster_set_variant(int variant); /* tuning knob: 0 = one pixel per lane (default), 1 = two pixels per lane */
+/* compositing variant for <= 4 colour channels, forward AND backward (set it before the forward, leave it until the
+ * backward has run): 0 = one pixel per lane (8x4 block per warp), 1 = two pixels per lane (8x8 block per warp) */
+void rs_raster_set_variant(int variant);
+int rs_raster_get_variant(void);
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
                  const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,
@@ -132,7 +135,9 @@ int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_pe
                      long long M, float* out_colors /* [C,H,W,D] */, float* out_alphas /* [C,H,W] */,
                      float* out_expected_depths, float* out_median_depths, float* out_normals /* [C,H,W,3] */,
                      float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream);
-/* Gradient record geom_grad[C*N,16] = (gx gy | ga gb gc | go | g_ray_t g_rpx g_rpy | gnx gny gnz | colour 0..3);
+/* Gradient record geom_grad[C*N,16] = (S v_sigma*dx, S v_sigma*dy | ga gb gc | S v_sigma | g_ray_t g_rpx g_rpy |
+ * gnx gny gnz | colour 0..3), S = sum over blended pixels; rs_unpack_geom_grad turns the three moments into the
+ * means2d and opacity gradients (per-Gaussian linear maps with the conic / ray plane / opacity of `geom`);
  * geom_grad, color_grad[rows,DP] (only needed when DP > 4) and abs_grad[C*N,2] (NULL = absgrad off) must be
  * zero-filled by the caller; gradients are accumulated.  out_colors is only read when ed_channel >= 0. */
 int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_per_cam, int D, int ed_channel,
@@ -145,7 +150,8 @@ int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_pe
 /* Splits the gradient record into the per-input gradients; undoes the opacity * compensation fusion
  * (v_compensations[C,N] = go * opacity, v_opacities = go * compensation, summed over cameras when the
  * opacities are [N]); v_colors4 (NULL ok) receives the colour gradient when the colours have <= 4 channels. */
-int rs_unpack_geom_grad(const float* geom_grad, const float* abs_grad /* NULL ok */, int C, int N,
+int rs_unpack_geom_grad(const float* geom_grad, const float* geom /* the rs_pack_geom records */,
+                        const float* abs_grad /* NULL ok */, int C, int N,
                         const float* opacities, int opac_per_cam, const float* compensations /* NULL ok */,
                         float* v_means2d, float* v_means2d_abs /* NULL ok */, float* v_conics, float* v_opacities,
                         float* v_compensations /* NULL ok */, float* v_ray_ts, float* v_ray_planes,

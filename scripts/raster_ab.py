@@ -1,5 +1,5 @@
-"""A/B of the forward compositing variants on BASELINE config 2 (run on a B200)."""
-import math, sys
+"""A/B of the compositing variants (forward + backward) on BASELINE config 2 (run on a B200)."""
+import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "collab-splats_b200")); sys.path.insert(0, str(ROOT))
@@ -11,21 +11,31 @@ lib = be.load()
 dev = torch.device("cuda:0")
 cfg = scenes.BASELINE_CONFIGS[2]
 gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
-p = [t.to(dev) for t in scenes.activate(gs, 3)]
+p = [t.to(dev).requires_grad_(True) for t in scenes.activate(gs, 3)]
 vmd, Kd = vm.to(dev), Ks.to(dev)
-def fwd():
-    with torch.no_grad():
-        return rasterization(*p, vmd, Kd, cfg.width, cfg.height, packed=False, sh_degree=3, render_mode="RGB+ED",
-                             rasterize_mode="antialiased", return_depth_normal=True)
+cot = None
+def step():
+    global cot
+    for t in p: t.grad = None
+    o = rasterization(*p, vmd, Kd, cfg.width, cfg.height, packed=False, sh_degree=3, render_mode="RGB+ED",
+                      rasterize_mode="antialiased", return_depth_normal=True)
+    if cot is None:
+        g = torch.Generator(device=dev).manual_seed(1)
+        cot = [torch.randn(t.shape, device=dev, generator=g) for t in o[:5]]
+    sum((a * b).sum() for a, b in zip(o[:5], cot)).backward()
+    return [t.detach() for t in o[:5]], [t.grad.clone() for t in p]
 ref = None
+default = lib.rs_raster_get_variant()
 for variant in (0, 1, 0, 1):
     lib.rs_raster_set_variant(variant)
-    for _ in range(3): o = fwd()
+    for _ in range(3): o, g = step()
     lib.rs_timing_enable(1)
-    for _ in range(10): o = fwd()
+    for _ in range(10): o, g = step()
     torch.cuda.synchronize()
     s = be.timing_collect(); lib.rs_timing_enable(0)
-    if ref is None: ref = [t.clone() for t in o[:5]]
-    err = max(float((a - b).abs().max()) for a, b in zip(o[:5], ref))
-    print(f"variant {variant}: rs_rasterize_fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms   max|diff vs variant 0| {err:.2e}")
-lib.rs_raster_set_variant(0)
+    if ref is None: ref = (o, g)
+    err = max(float((a - b).abs().max()) for a, b in zip(o, ref[0]))
+    gerr = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g, ref[1]))
+    print(f"variant {variant}: fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
+          f"unpack {s['rs_unpack_geom_grad'][0] / 10:.4f} ms   max|out diff vs first| {err:.2e}  max rel grad diff {gerr:.2e}")
+lib.rs_raster_set_variant(default)

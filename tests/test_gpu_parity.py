@@ -205,13 +205,30 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
                 ray_planes=ray_planes, normals=normals), offs, flat
 
 
+@pytest.fixture
+def raster_variant(request):
+    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane) for
+    the duration of a test and restores the library default afterwards."""
+    from radegs_b200 import backend as be
+    lib = be.load()
+    default = lib.rs_raster_get_variant()
+    lib.rs_raster_set_variant(request.param)
+    yield request.param
+    lib.rs_raster_set_variant(default)
+
+
+@pytest.mark.parametrize("raster_variant", [0, 1], indirect=True)
 @pytest.mark.parametrize("D,views,w,h,bg,n", [(3, 1, 160, 96, False, 2500), (4, 2, 100, 70, True, 2500),
                                                (17, 1, 96, 64, False, 2500), (67, 1, 64, 48, True, 2500),
                                                (8, 1, 64, 64, False, 2500),
                                                # > 256 Gaussians per tile: several staged batches per tile
-                                               (3, 1, 64, 48, False, 9000), (36, 1, 48, 32, False, 4000)])
-def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg, n):
+                                               (3, 1, 64, 48, False, 9000), (36, 1, 48, 32, False, 4000),
+                                               # image not a multiple of the tile / warp block
+                                               (2, 1, 75, 53, True, 3000)])
+def test_rasterize_to_pixels_fwd_bwd(cuda_dev, raster_variant, D, views, w, h, bg, n):
     from gsplat.cuda._wrapper import rasterize_to_pixels
+    if raster_variant == 1 and D > 4:
+        pytest.skip("the two-pixels-per-lane kernels cover <= 4 channels; wider rows use the generic kernels")
     cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views)
     inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, D)
     g = torch.Generator().manual_seed(9)
@@ -252,11 +269,12 @@ def test_rasterize_to_pixels_fwd_bwd(cuda_dev, D, views, w, h, bg, n):
         assert ok, msg
 
 
-def test_rasterize_absgrad_and_shared_colors(cuda_dev):
+@pytest.mark.parametrize("raster_variant,D", [(0, 5), (0, 3), (1, 3)], indirect=["raster_variant"])
+def test_rasterize_absgrad_and_shared_colors(cuda_dev, raster_variant, D):
     """colors [N,D] shared by all cameras (no expansion) and the absgrad side channel."""
     from gsplat.cuda._wrapper import rasterize_to_pixels
     cfg, gs, vm, Ks = small_scene(n=2000, w=96, h=64, views=2)
-    inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, 5)
+    inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, D)
     shared = inp["colors"][0].contiguous()
     cpu_col = shared.clone().requires_grad_(True)
     cpu_m2 = inp["means2d"].clone().requires_grad_(True)
