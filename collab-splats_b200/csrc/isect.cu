@@ -48,9 +48,10 @@ constexpr int SCAN_TILE = IB * SCAN_ITEMS;
 #define ST_PREFIX (2ull << 62)
 #define ST_MASK (3ull << 62)
 
+// `order` (optional): the scanned sequence is in[order[i]] (the presorted path scans tile counts in depth order)
 __global__ void __launch_bounds__(IB)
-scan_kernel(const int32_t* __restrict__ in, long long* __restrict__ out, long long n,
-            volatile unsigned long long* status, unsigned int* ticket) {
+scan_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ order, long long* __restrict__ out,
+            long long n, volatile unsigned long long* status, unsigned int* ticket) {
   __shared__ unsigned int s_tile;
   __shared__ long long s_warp[IB / 32];
   __shared__ long long s_excl;
@@ -60,7 +61,19 @@ scan_kernel(const int32_t* __restrict__ in, long long* __restrict__ out, long lo
   const long long tile = s_tile;
   const long long base = tile * SCAN_TILE + (long long)t * SCAN_ITEMS;
   int v[SCAN_ITEMS];
-  if (base + SCAN_ITEMS <= n) {
+  if (order) {
+    int idx[SCAN_ITEMS];
+    if (base + SCAN_ITEMS <= n) {
+      int4 a = __ldg(reinterpret_cast<const int4*>(order + base));
+      int4 b = __ldg(reinterpret_cast<const int4*>(order + base) + 1);
+      idx[0] = a.x; idx[1] = a.y; idx[2] = a.z; idx[3] = a.w; idx[4] = b.x; idx[5] = b.y; idx[6] = b.z; idx[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < SCAN_ITEMS; ++i) idx[i] = (base + i < n) ? __ldg(order + base + i) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = idx[i] >= 0 ? __ldg(in + idx[i]) : 0;
+  } else if (base + SCAN_ITEMS <= n) {
     int4 a = __ldg(reinterpret_cast<const int4*>(in + base));
     int4 b = __ldg(reinterpret_cast<const int4*>(in + base) + 1);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -152,6 +165,35 @@ isect_emit_kernel(const float2* __restrict__ means2d, const int2* __restrict__ r
     }
 }
 
+// Presorted path: thread p handles the p-th (camera, Gaussian) entry in DEPTH order (`order` = stable argsort of
+// the depth bits) and writes its tile keys at cum[p] - count, so the emitted stream is already sorted by
+// (depth, flatten id, tile y, tile x) -- exactly what the first four 8-bit passes of the LSD sort over the 64-bit
+// keys produce from the (flatten id, y, x) emission order.  Only the (camera | tile) bits remain to be sorted.
+__global__ void __launch_bounds__(IB)
+isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii,
+                          const float* __restrict__ depths, const int32_t* __restrict__ order,
+                          const long long* __restrict__ cum, int C, int N, int tile_w, int tile_h, int tile_bits,
+                          long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+  const long long p = (long long)blockIdx.x * IB + threadIdx.x;
+  if (p >= (long long)C * N) return;
+  const int e = __ldg(order + p);
+  int xmin, ymin, xmax, ymax;
+  if (!tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax)) return;
+  const int cnt = (xmax - xmin) * (ymax - ymin);
+  if (cnt <= 0) return;
+  long long pos = __ldg(cum + p) - cnt;
+  const long long cam = e / N;
+  const unsigned long long hi_cam = (unsigned long long)cam << (32 + tile_bits);
+  const unsigned long long dbits = (unsigned long long)__float_as_uint(__ldg(depths + e));
+  for (int y = ymin; y < ymax; ++y)
+    for (int x = xmin; x < xmax; ++x) {
+      unsigned long long tile = (unsigned long long)(y * tile_w + x);
+      isect_ids[pos] = (long long)(hi_cam | (tile << 32) | dbits);
+      flatten_ids[pos] = (int32_t)e;
+      ++pos;
+    }
+}
+
 __global__ void __launch_bounds__(IB)
 offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, int n_tiles, int tile_bits, int total,
                      int32_t* __restrict__ offsets) {
@@ -210,7 +252,23 @@ extern "C" int rs_cumsum_i32_i64(const int32_t* in, long long* out, long long n,
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
   unsigned int* ticket = (unsigned int*)temp;
   unsigned long long* status = (unsigned long long*)((char*)temp + 16);
-  scan_kernel<<<(unsigned)tiles, IB, 0, (cudaStream_t)stream>>>(in, out, n, status, ticket);
+  scan_kernel<<<(unsigned)tiles, IB, 0, (cudaStream_t)stream>>>(in, nullptr, out, n, status, ticket);
+  RS_RETURN_LAST_ERROR();
+}
+
+// out[i] = sum_{j <= i} in[order[j]]  (order: a permutation of 0..n-1)
+extern "C" int rs_cumsum_gather_i32_i64(const int32_t* in, const int32_t* order, long long* out, long long n,
+                                        void* temp, long long temp_bytes, void* stream) {
+  RsSpan span__("rs_cumsum_gather_i32_i64", stream);
+  if (n < 0) return RS_ERR_BAD_ARG;
+  if (n == 0) return RS_OK;
+  if (!in || !order || !out || !temp || temp_bytes < rs_cumsum_temp_bytes(n)) return RS_ERR_BAD_ARG;
+  long long tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)rs_cumsum_temp_bytes(n), (cudaStream_t)stream);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  unsigned int* ticket = (unsigned int*)temp;
+  unsigned long long* status = (unsigned long long*)((char*)temp + 16);
+  scan_kernel<<<(unsigned)tiles, IB, 0, (cudaStream_t)stream>>>(in, order, out, n, status, ticket);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -225,6 +283,23 @@ extern "C" int rs_isect_emit(const float* means2d, const int32_t* radii, const f
   int tile_bits = tile_bits_for((long long)tile_w * tile_h);
   isect_emit_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
       (const float2*)means2d, (const int2*)radii, depths, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
+      flatten_ids);
+  RS_RETURN_LAST_ERROR();
+}
+
+// order[C*N]: stable argsort of the depth bits (rs_argsort_u32); cum_tiles[p]: inclusive sum of the tile counts in
+// that order (rs_cumsum_gather_i32_i64).  The emitted pairs only need sorting on key bits [32, end_bit).
+extern "C" int rs_isect_emit_ordered(const float* means2d, const int32_t* radii, const float* depths,
+                                     const int32_t* order, const long long* cum_tiles, int C, int N, int tile_w,
+                                     int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream) {
+  RsSpan span__("rs_isect_emit_ordered", stream);
+  if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
+  if ((long long)C * N >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  if (C == 0 || N == 0) return RS_OK;
+  if (!means2d || !radii || !depths || !order || !cum_tiles || !isect_ids || !flatten_ids) return RS_ERR_BAD_ARG;
+  int tile_bits = tile_bits_for((long long)tile_w * tile_h);
+  isect_emit_ordered_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, (const int2*)radii, depths, order, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
       flatten_ids);
   RS_RETURN_LAST_ERROR();
 }

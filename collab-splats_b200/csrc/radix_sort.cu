@@ -21,6 +21,7 @@ constexpr int ST = 256;            // threads per block
 // items per thread: 8 (64 registers, 4 CTAs/SM, 2048-pair tiles) or 16 (98 registers, 2 CTAs/SM, 4096-pair tiles);
 // selectable at run time (rs_sort_set_items) so both can be measured on the same box
 static int g_sort_items = 8;
+static int g_sort_window = 4;      // look-back polling window (4, 8 or 16 predecessors per round trip)
 constexpr int SWARPS = ST / 32;
 constexpr int MAX_PASSES = 8;
 #define LB_AGG (1u << 30)
@@ -34,14 +35,15 @@ struct PassInfo {
   int n;
 };
 
+template <typename K>
 __global__ void __launch_bounds__(ST)
-radix_hist_kernel(const u64* __restrict__ keys, long long M, PassInfo pi, u32* __restrict__ ghist) {
+radix_hist_kernel(const K* __restrict__ keys, long long M, PassInfo pi, u32* __restrict__ ghist) {
   __shared__ u32 sh[MAX_PASSES * RADIX];
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += ST) sh[i] = 0;
   __syncthreads();
   const long long stride = (long long)gridDim.x * ST;
   for (long long i = (long long)blockIdx.x * ST + threadIdx.x; i < M; i += stride) {
-    u64 k = __ldg(keys + i);
+    K k = __ldg(keys + i);
 #pragma unroll
     for (int p = 0; p < MAX_PASSES; ++p)
       if (p < pi.n) atomicAdd(&sh[p * RADIX + (u32)((k >> pi.shift[p]) & pi.mask[p])], 1u);
@@ -68,9 +70,10 @@ __device__ __forceinline__ u32 block_inclusive_scan(u32 v, u32* s_warp, int lane
   return v + off;
 }
 
-template <int SI>
+// K = u64 (tile|depth keys) or u32 (depth keys of the presorted path); vin == nullptr: the value of pair i is i
+template <typename K, int SI, int LB_WINDOW>
 __global__ void __launch_bounds__(ST, (SI == 8 ? 4 : 2))
-radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u64* __restrict__ kout,
+radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
                      u32* __restrict__ vout, int M, int shift, u32 mask, const u32* __restrict__ ghist,
                      volatile u32* status, u32* ticket) {
   __shared__ u32 s_cnt[SWARPS][RADIX];
@@ -79,7 +82,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
   __shared__ u32 s_warp[SWARPS];
   __shared__ u32 s_tile;
   constexpr int STILE = ST * SI;
-  __shared__ __align__(16) u64 s_keys[STILE];
+  __shared__ __align__(16) K s_keys[STILE];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
@@ -90,14 +93,14 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
   const int n_valid = min(STILE, M - tile_base);
 
   // ---- load (warp-contiguous, index order = (round, lane) inside each warp's 512-pair slice)
-  u64 key[SI];
+  K key[SI];
   u32 val[SI];
 #pragma unroll
   for (int r = 0; r < SI; ++r) {
     const int i = warp * (32 * SI) + r * 32 + lane;
     const bool ok = i < n_valid;
-    key[r] = ok ? __ldg(kin + tile_base + i) : ~0ull;
-    val[r] = ok ? __ldg(vin + tile_base + i) : 0u;
+    key[r] = ok ? __ldg(kin + tile_base + i) : (K)~(K)0;
+    val[r] = ok ? (vin ? __ldg(vin + tile_base + i) : (u32)(tile_base + i)) : 0u;
   }
   // ---- warp-local stable ranks
   u32 pos[SI];
@@ -142,16 +145,16 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
     s_keys[pos[r]] = key[r];
   }
   // ---- decoupled look-back (thread t <-> digit t): sum of the digit's counts over all earlier tiles.
-  //      Four predecessors are polled at once (independent loads in flight) and consumed in order, so a chain
-  //      of k aggregate-only predecessors costs ~k/4 memory round trips instead of k.
+  //      LB_WINDOW predecessors are polled at once (independent loads in flight) and consumed in order, so a chain
+  //      of k aggregate-only predecessors costs ~k/LB_WINDOW memory round trips instead of k.
   u32 excl_prev = 0;
   {
     int p = tile - 1;
     bool found = (tile == 0);
     while (!found) {
-      u32 sv[4];
+      u32 sv[LB_WINDOW];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < LB_WINDOW; ++i) {
         sv[i] = LB_PREFIX;  // before the first tile: an empty inclusive prefix
         if (p - i >= 0) {
           const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
@@ -159,7 +162,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
         }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < LB_WINDOW; ++i) {
         if (found) break;
         while ((sv[i] & LB_FLAGS) == 0u) {  // not published yet: poll this one
           const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
@@ -168,7 +171,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
         excl_prev += sv[i] & LB_VALUE;
         found = (sv[i] & LB_FLAGS) == LB_PREFIX;
       }
-      p -= 4;
+      p -= LB_WINDOW;
     }
   }
   if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
@@ -179,7 +182,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
 #pragma unroll
   for (int i = 0; i < SI; ++i) {
     const int p = i * ST + t;
-    const u64 k = s_keys[p];
+    const K k = s_keys[p];
     const u32 d = (u32)((k >> shift) & mask);
     out[i] = s_gbase[d] + p;
     if (p < n_valid) kout[out[i]] = k;
@@ -201,6 +204,7 @@ radix_scatter_kernel(const u64* __restrict__ kin, const u32* __restrict__ vin, u
 static long long sort_blocks(long long M, int items) { return (M + ST * items - 1) / (ST * items); }
 
 extern "C" void rs_sort_set_items(int items) { g_sort_items = (items == 16) ? 16 : 8; }
+extern "C" void rs_sort_set_window(int w) { g_sort_window = (w == 16) ? 16 : (w == 8 ? 8 : 4); }
 
 extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit) {
   int npass = end_bit > begin_bit ? (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS : 0;
@@ -209,17 +213,15 @@ extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int en
   return (long long)MAX_PASSES * RADIX * 4 + 256 + (long long)npass * nb * RADIX * 4;
 }
 
-// Sorts M pairs by key bits [begin_bit, end_bit), stable, ascending.  Both buffer pairs are clobbered.
-// Returns 0 if the sorted pairs are in (keys_b, vals_b), 1 if they are in (keys_a, vals_a), < 0 on error.
-extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
-                             int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
-  RsSpan span__("rs_sort_pairs", stream);
-  if (M < 0 || begin_bit < 0 || end_bit > 64) return RS_ERR_BAD_ARG;
+template <typename K>
+static int sort_pairs_impl(K* ka, u32* va, K* kb, u32* vb, bool iota_vals, long long M, int begin_bit, int end_bit,
+                           void* temp, long long temp_bytes, void* stream) {
+  if (M < 0 || begin_bit < 0 || end_bit > (int)(8 * sizeof(K))) return RS_ERR_BAD_ARG;
   if (M >= (1ll << 30)) return RS_ERR_UNSUPPORTED;  // look-back words carry 30-bit counts
   if (M == 0 || end_bit <= begin_bit) return 1;
   const int npass = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
   if (npass > MAX_PASSES) return RS_ERR_BAD_ARG;
-  if (!keys_a || !vals_a || !keys_b || !vals_b || !temp || temp_bytes < rs_sort_pairs_temp_bytes(M, begin_bit, end_bit))
+  if (!ka || (!va && !iota_vals) || !kb || !vb || !temp || temp_bytes < rs_sort_pairs_temp_bytes(M, begin_bit, end_bit))
     return RS_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   PassInfo pi;
@@ -240,23 +242,40 @@ extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys
   u32* status = (u32*)((char*)temp + MAX_PASSES * RADIX * 4 + 256);
   int hist_blocks = (int)(nblocks < 148 * 8 ? nblocks : 148 * 8);
   const long long status_stride = sort_blocks(M, 8) * RADIX;
-  radix_hist_kernel<<<hist_blocks, ST, 0, st>>>((const u64*)keys_a, M, pi, ghist);
-  u64* ka = (u64*)keys_a; u64* kb = (u64*)keys_b;
-  u32* va = (u32*)vals_a; u32* vb = (u32*)vals_b;
+  radix_hist_kernel<K><<<hist_blocks, ST, 0, st>>>(ka, M, pi, ghist);
   for (int p = 0; p < npass; ++p) {
-    if (items == 16)
-      radix_scatter_kernel<16><<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
-                                                                ghist + p * RADIX, status + (size_t)p * status_stride,
-                                                                tickets + p);
-    else
-      radix_scatter_kernel<8><<<(unsigned)nblocks, ST, 0, st>>>(ka, va, kb, vb, (int)M, pi.shift[p], pi.mask[p],
-                                                               ghist + p * RADIX, status + (size_t)p * status_stride,
-                                                               tickets + p);
-    u64* tk = ka; ka = kb; kb = tk;
+    const u32* vin = (p == 0 && iota_vals) ? nullptr : va;
+#define RS_LAUNCH_SCATTER(SI, LBW)                                                                              \
+  radix_scatter_kernel<K, SI, LBW><<<(unsigned)nblocks, ST, 0, st>>>(ka, vin, kb, vb, (int)M, pi.shift[p],      \
+                                                                     pi.mask[p], ghist + p * RADIX,             \
+                                                                     status + (size_t)p * status_stride, tickets + p)
+    if (items == 16) { if (g_sort_window == 16) RS_LAUNCH_SCATTER(16, 16); else if (g_sort_window == 8) RS_LAUNCH_SCATTER(16, 8); else RS_LAUNCH_SCATTER(16, 4); }
+    else { if (g_sort_window == 16) RS_LAUNCH_SCATTER(8, 16); else if (g_sort_window == 8) RS_LAUNCH_SCATTER(8, 8); else RS_LAUNCH_SCATTER(8, 4); }
+#undef RS_LAUNCH_SCATTER
+    K* tk = ka; ka = kb; kb = tk;
     u32* tv = va; va = vb; vb = tv;
   }
   rs_count_launches(1 + npass);
   e = cudaPeekAtLastError();
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
   return (npass & 1) ? 0 : 1;
+}
+
+// Sorts M pairs by key bits [begin_bit, end_bit), stable, ascending.  Both buffer pairs are clobbered.
+// Returns 0 if the sorted pairs are in (keys_b, vals_b), 1 if they are in (keys_a, vals_a), < 0 on error.
+extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
+                             int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
+  RsSpan span__("rs_sort_pairs", stream);
+  return sort_pairs_impl<u64>((u64*)keys_a, (u32*)vals_a, (u64*)keys_b, (u32*)vals_b, false, M, begin_bit, end_bit,
+                              temp, temp_bytes, stream);
+}
+
+// Same for 32-bit keys (the depth keys of the presorted intersection path).  vals_a's CONTENT is not read: the
+// value of pair i is i (an argsort); vals_a is still needed as the second ping-pong buffer.
+extern "C" int rs_argsort_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32_t* vals_b, long long M,
+                              int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
+  RsSpan span__("rs_argsort_u32", stream);
+  if (!vals_a) return RS_ERR_BAD_ARG;
+  return sort_pairs_impl<u32>((u32*)keys_a, (u32*)vals_a, (u32*)keys_b, (u32*)vals_b, true, M, begin_bit, end_bit,
+                              temp, temp_bytes, stream);
 }

@@ -38,6 +38,9 @@ _SIGNATURES = {
     "rs_cumsum_i32_i64": (_i, [_p, _p, _ll, _p, _ll, _p]),
     "rs_isect_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_offset_encode": (_i, [_p, _ll, _i, _i, _i, _p, _p]),
+    "rs_cumsum_gather_i32_i64": (_i, [_p, _p, _p, _ll, _p, _ll, _p]),
+    "rs_isect_emit_ordered": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "rs_argsort_u32": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_tile_sort_max_segment": (_i, []),
     "rs_isect_tile_count": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_isect_tile_scan": (_i, [_p, _i, _p, _p, _p, _p]),
@@ -45,6 +48,7 @@ _SIGNATURES = {
     "rs_isect_tile_sort": (_i, [_p, _p, _i, _i, _i, _ll, _i, _p, _p, _p]),
     "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
     "rs_sort_set_items": (None, [_i]),
+    "rs_sort_set_window": (None, [_i]),
     "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_raster_padded_channels": (_i, [_i]),
     "rs_raster_set_stats": (None, [_p]),

@@ -88,6 +88,15 @@ int rs_isect_emit(const float* means2d, const int32_t* radii, const float* depth
                   int C, int N, int tile_w, int tile_h, long long* isect_ids, int32_t* flatten_ids, void* stream);
 int rs_offset_encode(const long long* sorted_isect_ids, long long M, int C, int tile_w, int tile_h,
                      int32_t* offsets /* [C,tile_h,tile_w] */, void* stream);
+/* Depth-presorted emission (default inside isect_tiles(sort=True); same sorted output, bit for bit): the LSD sort's
+ * four depth passes over the M intersections are replaced by one stable argsort of the C*N depth bits
+ * (rs_argsort_u32 -> order), the tile counts are scanned in that order (rs_cumsum_gather_i32_i64) and the keys are
+ * emitted in that order (rs_isect_emit_ordered); only key bits [32, end_bit) then remain for rs_sort_pairs. */
+int rs_cumsum_gather_i32_i64(const int32_t* in, const int32_t* order, long long* out_inclusive, long long n,
+                             void* temp, long long temp_bytes, void* stream);
+int rs_isect_emit_ordered(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
+                          const long long* cum_tiles_in_order, int C, int N, int tile_w, int tile_h,
+                          long long* isect_ids, int32_t* flatten_ids, void* stream);
 
 /* ---- tile-partitioned fast path for isect_tiles(sort=True) + isect_offset_encode (same outputs, bit for bit):
  * per-tile histogram -> exclusive scan = tile offsets -> atomic-slot emission of (depth<<32 | flatten id) into the
@@ -108,8 +117,13 @@ int rs_isect_tile_sort(const unsigned long long* pairs, const int32_t* offsets, 
  * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */
 long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit);
 void rs_sort_set_items(int items_per_thread); /* tuning knob: 8 (default) or 16 keys per thread */
+void rs_sort_set_window(int predecessors);    /* tuning knob: look-back polling window 4 (default), 8 or 16 */
 int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
                   int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream);
+/* Stable argsort of 32-bit keys: same contract and temp size (rs_sort_pairs_temp_bytes), but the value of pair i
+ * is i; vals_a is only scratch (the second ping-pong buffer). */
+int rs_argsort_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32_t* vals_b, long long M, int begin_bit,
+                   int end_bit, void* temp, long long temp_bytes, void* stream);
 
 /* ---- compositing: replaces gsplat-rade rasterize_to_pixels fwd/bwd.
  * Inputs are first packed: geom[C*N,16] (rs_pack_geom) and colours padded to DP = rs_raster_padded_channels(D)

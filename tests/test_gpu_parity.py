@@ -160,8 +160,39 @@ def test_radix_sort_pairs(cuda_dev, m, end_bit):
     assert torch.equal(ko.cpu(), keys[torch.from_numpy(order)])
 
 
+@pytest.mark.parametrize("m", [1, 31, 2048, 2049, 100_003, 1_000_000])
+def test_argsort_u32(cuda_dev, m):
+    """rs_argsort_u32 (depth keys of the presorted intersection path) = a stable argsort, ties included."""
+    from radegs_b200 import backend as be
+    lib = be.load()
+    g = torch.Generator().manual_seed(m)
+    depth = torch.rand(m, generator=g) * 5.0 + 0.01
+    depth[torch.rand(m, generator=g) < 0.3] = 2.5            # many equal keys: stability matters
+    keys = depth.view(torch.int32)
+    order = np.argsort(keys.numpy().astype(np.uint32), kind="stable")
+    ka = keys.to(cuda_dev).clone()
+    kb, va, vb = torch.empty_like(ka), torch.empty_like(ka), torch.empty_like(ka)
+    tb = lib.rs_sort_pairs_temp_bytes(m, 0, 32)
+    temp = torch.empty(tb, device=cuda_dev, dtype=torch.uint8)
+    where = be.check(lib.rs_argsort_u32(be.ptr(ka), be.ptr(va), be.ptr(kb), be.ptr(vb), m, 0, 32, be.ptr(temp), tb,
+                                        be.stream_ptr(cuda_dev)), "argsort")
+    ko, vo = (kb, vb) if where == 0 else (ka, va)
+    assert torch.equal(vo.cpu().long(), torch.from_numpy(order)), "not the stable argsort"
+    assert torch.equal(ko.cpu(), keys[torch.from_numpy(order)])
+
+
+@pytest.fixture
+def isect_method(request):
+    import gsplat.cuda._wrapper as wr
+    default = wr.ISECT_SORT_METHOD
+    wr.ISECT_SORT_METHOD = request.param
+    yield request.param
+    wr.ISECT_SORT_METHOD = default
+
+
+@pytest.mark.parametrize("isect_method", ["presort", "radix"], indirect=True)
 @pytest.mark.parametrize("views,w,h", [(1, 160, 96), (2, 250, 130), (5, 64, 64)])
-def test_isect_bit_exact(cuda_dev, views, w, h):
+def test_isect_bit_exact(cuda_dev, isect_method, views, w, h):
     """Stage-wise (oracle consumes the GPU's own floats) and end to end (oracle's own projection)."""
     from gsplat.cuda._wrapper import fully_fused_projection, isect_offset_encode, isect_tiles
     cfg, gs, vm, Ks = small_scene(n=6000, w=w, h=h, views=views, spread=1.4)
@@ -187,6 +218,23 @@ def test_isect_bit_exact(cuda_dev, views, w, h):
     o_radii, o_m2, o_depths = O.fully_fused_projection(means, quats, scales, vm, Ks, w, h)[:3]
     e_tiles, e_ids, e_flat = O.isect_tiles(o_m2, o_radii, o_depths, 16, tw, th)
     assert torch.equal(ids.cpu(), e_ids) and torch.equal(flat.cpu(), e_flat) and torch.equal(tiles.cpu(), e_tiles)
+
+
+@pytest.mark.parametrize("isect_method", ["presort", "radix"], indirect=True)
+def test_isect_equal_depths_stable(cuda_dev, isect_method):
+    """Many Gaussians share a depth (quantised to 1/8): the order inside a tile is then decided by stability alone
+    (flatten id, tile row, tile column), which the depth-presorted path must reproduce bit for bit."""
+    from gsplat.cuda._wrapper import isect_tiles
+    views, w, h = 3, 200, 120
+    cfg, gs, vm, Ks = small_scene(n=8000, w=w, h=h, views=views, spread=1.3)
+    means, quats, scales, _, _ = scenes.activate(gs, 3)
+    radii, m2, depths = O.fully_fused_projection(means, quats, scales, vm, Ks, w, h)[:3]
+    depths = (depths * 8).round() / 8
+    tw, th = math.ceil(w / 16), math.ceil(h / 16)
+    r_tiles, r_ids, r_flat = O.isect_tiles(m2, radii, depths, 16, tw, th)
+    tiles, ids, flat = isect_tiles(m2.to(cuda_dev), radii.to(cuda_dev), depths.to(cuda_dev), 16, tw, th)
+    assert int((r_ids[1:] == r_ids[:-1]).sum()) > 1000, "the scene must contain equal keys"
+    assert torch.equal(tiles.cpu(), r_tiles) and torch.equal(ids.cpu(), r_ids) and torch.equal(flat.cpu(), r_flat)
 
 
 # ------------------------------------------------------------------------------------------------ compositing
