@@ -33,11 +33,13 @@ pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ c
                  const float* __restrict__ opacities, int opac_per_cam, const float* __restrict__ compensations,
                  int N, const float* __restrict__ ray_ts, const float2* __restrict__ ray_planes,
                  const float* __restrict__ normals, const int2* __restrict__ radii, long long n_elems,
-                 float4* __restrict__ geom) {
+                 int cull_mode, float4* __restrict__ geom) {
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
   if (e >= n_elems) return;
-  float4 q0 = make_float4(0.f, 0.f, -1e30f, -1e30f), q1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f), q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // a culled Gaussian never passes either footprint test (mode 0: negative extents; mode 1: tau' = -inf)
+  float4 q0 = make_float4(0.f, 0.f, cull_mode == 0 ? -1e30f : 0.f, cull_mode == 0 ? -1e30f : 0.f);
+  float4 q1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f), q3 = make_float4(0.f, 0.f, 0.f, -1e30f);
   bool live = true;
   if (radii) { int2 r = __ldg(radii + e); live = r.x > 0 && r.y > 0; }
   if (live) {
@@ -45,25 +47,35 @@ pack_geom_kernel(const float2* __restrict__ means2d, const float* __restrict__ c
     float a = __ldg(conics + e * 3), b = __ldg(conics + e * 3 + 1), c = __ldg(conics + e * 3 + 2);
     float o = __ldg(opacities + (opac_per_cam ? e : e % N));
     if (compensations) o *= __ldg(compensations + e);  // antialiased mode: opacity * sqrt(det0/det)
-    // footprint of alpha >= 1/255: sigma <= tau = ln(255 o); bbox half extents sqrt(2 tau Sigma_ii), padded
-    // so that the test can only ever keep more pairs than the exact per-pair test would
-    float hx = 1e30f, hy = 1e30f;
+    // footprint of alpha >= 1/255: sigma <= tau = ln(255 o).  Two conservative tests are supported (both can only
+    // ever keep more pairs than the exact per-pair test would):
+    //  cull_mode 0: bbox half extents sqrt(2 tau Sigma_ii) of the footprint ellipse, padded -> (hx, hy);
+    //  cull_mode 1: exact ellipse-vs-rectangle test: sigma' (log2 units) is minimised over the rectangle of pixel
+    //               centres (on the one or two edges facing the centre) and compared with tau' = log2(255 o) padded;
+    //               the record carries the two edge-minimiser slopes (-b'/2c', -b'/2a') and tau'.
+    float hx = 1e30f, hy = 1e30f, taup = 1e30f;
     float tau = logf(255.f * o);
     if (tau < -0.02f) {
-      hx = -1e30f; hy = -1e30f;  // alpha < 1/255 everywhere
+      hx = -1e30f; hy = -1e30f; taup = -1e30f;  // alpha < 1/255 everywhere
     } else if (tau == tau) {
       float det = a * c - b * b;
-      if (det > 0.f && isfinite(det)) {
-        float s = 2.f * (tau + 0.03f) / det;
-        float ex = sqrtf(s * c) * 1.001f + 0.02f, ey = sqrtf(s * a) * 1.001f + 0.02f;
-        if (isfinite(ex) && isfinite(ey)) { hx = ex; hy = ey; }
-      }
-    }
+      if (det > 0.f && isfinite(det) && a > 0.f && c > 0.f) {
+        if (cull_mode == 0) {
+          float s = 2.f * (tau + 0.03f) / det;
+          float ex = sqrtf(s * c) * 1.001f + 0.02f, ey = sqrtf(s * a) * 1.001f + 0.02f;
+          if (isfinite(ex) && isfinite(ey)) { hx = ex; hy = ey; }
+        } else {
+          float rx = -b / c, ry = -b / a;   // = -b'/(2c'), -b'/(2a') with the pre-scaled conic
+          float tp = (tau + 0.03f) * RS_LOG2E * 1.0001f + 0.01f;
+          if (isfinite(rx) && isfinite(ry) && isfinite(tp)) { hx = rx; hy = ry; taup = tp; } else { hx = 0.f; hy = 0.f; }
+        }
+      } else if (cull_mode != 0) { hx = 0.f; hy = 0.f; }
+    } else if (cull_mode != 0) { hx = 0.f; hy = 0.f; }
     q0 = make_float4(m.x, m.y, hx, hy);
     q1 = make_float4(0.5f * RS_LOG2E * a, RS_LOG2E * b, 0.5f * RS_LOG2E * c, o);
     float2 rp = __ldg(ray_planes + e);
     q2 = make_float4(__ldg(ray_ts + e), rp.x, rp.y, 0.f);  // .w is overwritten with the flatten id below
-    q3 = make_float4(__ldg(normals + e * 3), __ldg(normals + e * 3 + 1), __ldg(normals + e * 3 + 2), 0.f);
+    q3 = make_float4(__ldg(normals + e * 3), __ldg(normals + e * 3 + 1), __ldg(normals + e * 3 + 2), taup);
   }
   q2.w = __int_as_float((int)e);  // the record carries its own flatten id (bit pattern, never used as a float)
   geom[e * 4 + 0] = q0; geom[e * 4 + 1] = q1; geom[e * 4 + 2] = q2; geom[e * 4 + 3] = q3;
@@ -157,6 +169,7 @@ struct RasterArgs {
   const float* Ks;           // [C][9]
   int C, N, W, H, tile_w, tile_h, D, color_per_cam;
   int ed_channel;            // >= 0: that colour channel is divided by max(alpha, 1e-10) ("ED" modes); -1: none
+  int exact_cull;            // footprint test the records were packed for (rs_pack_geom's cull mode)
   const int* offsets;        // [C*tile_h*tile_w]
   const int* flatten_ids;    // [M]
   int M;
@@ -184,6 +197,27 @@ template <int DP, int BATCH> struct Smem {
   int ids[2][BATCH];
   int red[8];
 };
+
+// Footprint test of ONE Gaussian (per lane) against the warp's rectangle of pixel centres
+// [rcx - hw, rcx + hw] x [rcy - hh, rcy + hh].  Conservative in both modes (see pack_geom_kernel).
+template <int DP, int BATCH>
+__device__ __forceinline__ bool footprint_hit(const Smem<DP, BATCH>& s, int buf, int j, bool exact, float rcx, float rcy,
+                                              float hw, float hh) {
+  const float4 f = s.q0[buf][j];
+  const float cx = f.x - rcx, cy = f.y - rcy;   // d = centre - pixel ranges over [cx - hw, cx + hw] x [cy - hh, cy + hh]
+  if (!exact) return fabsf(cx) <= f.z + hw && fabsf(cy) <= f.w + hh;
+  const float4 q = s.q1[buf][j];
+  const float taup = s.q3[buf][j].w;
+  const float xlo = cx - hw, xhi = cx + hw, ylo = cy - hh, yhi = cy + hh;
+  const float dxe = fminf(fmaxf(0.f, xlo), xhi), dye = fminf(fmaxf(0.f, ylo), yhi);   // closest approach per axis
+  // minimum of sigma' over the vertical line x = dxe (clamped to the rectangle) and the horizontal line y = dye:
+  // the constrained minimum of a convex quadratic over a box lies on an edge facing its centre
+  const float dyv = fminf(fmaxf(f.z * dxe, ylo), yhi);
+  const float dxh = fminf(fmaxf(f.w * dye, xlo), xhi);
+  const float sv = fmaf(fmaf(q.z, dyv, q.y * dxe), dyv, q.x * dxe * dxe);
+  const float sh = fmaf(fmaf(q.x, dxh, q.y * dye), dxh, q.z * dye * dye);
+  return fminf(sv, sh) <= taup;
+}
 
 // gather one batch (ids already in s.ids[buf]) with 16-byte cp.async copies; consecutive threads copy
 // consecutive 16-byte chunks of one record, so each 64-byte record is one coalesced request
@@ -285,8 +319,7 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
         const int j = g0 + lane;
         bool hit = false;
         if (j < bcount) {
-          const float4 f = s.q0[buf][j];
-          hit = fabsf(f.x - c.rcx) <= f.z + 3.5f && fabsf(f.y - c.rcy) <= f.w + 1.5f;
+          hit = footprint_hit(s, buf, j, a.exact_cull != 0, c.rcx, c.rcy, 3.5f, 1.5f);
         }
         unsigned m = __ballot_sync(RS_FULL_MASK, hit);
         while (m) {
@@ -453,8 +486,7 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
         const int j = g0 + lane;
         bool hit = false;
         if (j < bcount) {
-          const float4 f = s.q0[buf][j];
-          hit = fabsf(f.x - rcx) <= f.z + 3.5f && fabsf(f.y - rcy) <= f.w + 3.5f;
+          hit = footprint_hit(s, buf, j, a.exact_cull != 0, rcx, rcy, 3.5f, 3.5f);
         }
         unsigned m = __ballot_sync(RS_FULL_MASK, hit);
         while (m) {
@@ -651,8 +683,7 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
       const int j = g0 + lane;
       bool hit = false;
       if (j <= hi) {
-        const float4 f = s.q0[buf][j];
-        hit = fabsf(f.x - c.rcx) <= f.z + 3.5f && fabsf(f.y - c.rcy) <= f.w + 1.5f;
+        hit = footprint_hit(s, buf, j, a.exact_cull != 0, c.rcx, c.rcy, 3.5f, 1.5f);
       }
       unsigned m = __ballot_sync(RS_FULL_MASK, hit);
       while (m) {
@@ -852,8 +883,7 @@ __global__ void __launch_bounds__(RT2, 4) rasterize_bwd2_kernel(const RasterArgs
       const int j = g0 + lane;
       bool hit = false;
       if (j <= hi) {
-        const float4 f = s.q0[buf][j];
-        hit = fabsf(f.x - rcx) <= f.z + 3.5f && fabsf(f.y - rcy) <= f.w + 3.5f;
+        hit = footprint_hit(s, buf, j, a.exact_cull != 0, rcx, rcy, 3.5f, 3.5f);
       }
       unsigned m = __ballot_sync(RS_FULL_MASK, hit);
       while (m) {
@@ -980,6 +1010,7 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
 }
 
 static unsigned long long* g_raster_stats = nullptr;
+static int g_cull_mode = 1;  // 0: bbox of the footprint ellipse; 1 (default): exact ellipse-vs-rectangle test
 template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
   const size_t smem = sizeof(Smem<DP, B>);
@@ -1024,6 +1055,10 @@ extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 // tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
 extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
 extern "C" int rs_raster_get_variant(void) { return g_raster_variant; }
+// footprint test used by rs_pack_geom AND the compositing kernels (set it before rs_pack_geom and leave it until
+// the backward has run): 0 = padded bbox of the alpha >= 1/255 ellipse, 1 (default) = exact ellipse-vs-rectangle
+extern "C" void rs_raster_set_cull_mode(int m) { g_cull_mode = m ? 1 : 0; }
+extern "C" int rs_raster_get_cull_mode(void) { return g_cull_mode; }
 
 // Work counters for the roofline arithmetic (bench.py): while `dev_counters` (4 x u64, device, zeroed by the caller)
 // is set, forward launches with <= 4 colour channels run an instrumented kernel that adds
@@ -1040,7 +1075,7 @@ extern "C" int rs_pack_geom(const float* means2d, const float* conics, const flo
   if (!means2d || !conics || !opacities || !ray_ts || !ray_planes || !normals || !geom) return RS_ERR_BAD_ARG;
   pack_geom_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
       (const float2*)means2d, conics, opacities, opac_per_cam, compensations, N, ray_ts, (const float2*)ray_planes,
-      normals, (const int2*)radii, n_elems, (float4*)geom);
+      normals, (const int2*)radii, n_elems, g_cull_mode, (float4*)geom);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -1095,6 +1130,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
   a.ed_channel = ed_channel;
+  a.exact_cull = g_cull_mode;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
@@ -1128,6 +1164,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
   a.ed_channel = ed_channel;
+  a.exact_cull = g_cull_mode;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = (float*)out_colors;
   a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;

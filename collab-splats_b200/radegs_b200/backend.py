@@ -54,6 +54,8 @@ _SIGNATURES = {
     "rs_raster_set_stats": (None, [_p]),
     "rs_raster_set_variant": (None, [_i]),
     "rs_raster_get_variant": (_i, []),
+    "rs_raster_set_cull_mode": (None, [_i]),
+    "rs_raster_get_cull_mode": (_i, []),
     "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "rs_pack_colors": (_i, [_p, _ll, _i, _i, _p, _p]),
     "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_p]),

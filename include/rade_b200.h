@@ -136,6 +136,11 @@ void rs_raster_set_stats(unsigned long long* dev_counters);
  * backward has run): 0 = one pixel per lane (8x4 block per warp), 1 = two pixels per lane (8x8 block per warp) */
 void rs_raster_set_variant(int variant);
 int rs_raster_get_variant(void);
+/* footprint (alpha >= 1/255) test the records are packed for and the kernels apply per (warp, Gaussian): 0 = padded
+ * bbox of the footprint ellipse, 1 (default) = exact ellipse-vs-rectangle test.  Both are conservative, so results
+ * do not depend on it.  Set it before rs_pack_geom and leave it until the backward has run. */
+void rs_raster_set_cull_mode(int mode);
+int rs_raster_get_cull_mode(void);
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
                  const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,

@@ -26,8 +26,8 @@ def step():
     return [t.detach() for t in o[:5]], [t.grad.clone() for t in p]
 ref = None
 default = lib.rs_raster_get_variant()
-for variant in (0, 1, 0, 1):
-    lib.rs_raster_set_variant(variant)
+for variant, cull in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 0), (1, 1)):
+    lib.rs_raster_set_variant(variant); lib.rs_raster_set_cull_mode(cull)
     for _ in range(3): o, g = step()
     lib.rs_timing_enable(1)
     for _ in range(10): o, g = step()
@@ -36,6 +36,6 @@ for variant in (0, 1, 0, 1):
     if ref is None: ref = (o, g)
     err = max(float((a - b).abs().max()) for a, b in zip(o, ref[0]))
     gerr = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g, ref[1]))
-    print(f"variant {variant}: fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
+    print(f"variant {variant} cull {cull}: fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
           f"unpack {s['rs_unpack_geom_grad'][0] / 10:.4f} ms   max|out diff vs first| {err:.2e}  max rel grad diff {gerr:.2e}")
-lib.rs_raster_set_variant(default)
+lib.rs_raster_set_variant(default); lib.rs_raster_set_cull_mode(1)

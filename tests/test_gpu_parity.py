@@ -255,17 +255,20 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
 
 @pytest.fixture
 def raster_variant(request):
-    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane) for
-    the duration of a test and restores the library default afterwards."""
+    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane; +10:
+    with the bbox footprint test instead of the exact ellipse-vs-rectangle one) for the duration of a test and
+    restores the library defaults afterwards."""
     from radegs_b200 import backend as be
     lib = be.load()
-    default = lib.rs_raster_get_variant()
-    lib.rs_raster_set_variant(request.param)
-    yield request.param
+    default, default_cull = lib.rs_raster_get_variant(), lib.rs_raster_get_cull_mode()
+    lib.rs_raster_set_variant(request.param % 10)
+    lib.rs_raster_set_cull_mode(0 if request.param >= 10 else 1)
+    yield request.param % 10
     lib.rs_raster_set_variant(default)
+    lib.rs_raster_set_cull_mode(default_cull)
 
 
-@pytest.mark.parametrize("raster_variant", [0, 1], indirect=True)
+@pytest.mark.parametrize("raster_variant", [0, 1, 10, 11], indirect=True)
 @pytest.mark.parametrize("D,views,w,h,bg,n", [(3, 1, 160, 96, False, 2500), (4, 2, 100, 70, True, 2500),
                                                (17, 1, 96, 64, False, 2500), (67, 1, 64, 48, True, 2500),
                                                (8, 1, 64, 64, False, 2500),
