@@ -166,6 +166,126 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
   smem_to_rows(s_out, v_coeffs + (size_t)n0 * row, count, row, RS, t);
 }
 
+
+// ------------------------------------------------------------------------------------------------ camera-sharded split
+// Multi-GPU (camera-sharded) form of the backward.  The SH-coefficient gradient of one camera is the outer product
+// Y_k(dir(n, camera)) x v_rgb[n]: 48 floats per Gaussian that carry 3 floats of information.  So instead of
+// all-reducing 192 B per Gaussian, every rank publishes its masked colour gradients (16 B per Gaussian and camera)
+// in peer-visible memory and every rank rebuilds the SUM OVER ALL CAMERAS OF ALL RANKS of the outer products
+// itself, reading the other ranks' rows straight over NVLink (or from an all-gathered copy):
+//   sh_colors_bwd_local_kernel : v_colors4 -> vrgb[C,N] (float4: clamp/visibility-masked rgb gradient, w = 0),
+//                                v_means (direction part), v_depths; also writes the camera positions to the header
+//   sh_coeffs_gather_kernel    : v_coeffs[n,k,:] = sum over sources (rank g, camera c) of Y_k(dir(n, campos_gc)) *
+//                                vrgb_gc[n,:], in a fixed (g, c) order, so every rank gets bit-identical sums.
+// A source region is [header: RS_PEER_HEADER_BYTES, float4 campos per camera][float4 vrgb[cams][N]].
+constexpr int RS_PEER_HEADER_BYTES = 1024;  // up to 64 cameras per rank
+constexpr int RS_MAX_PEERS = 16;
+
+struct PeerSources {
+  const char* base[RS_MAX_PEERS];
+  int cams[RS_MAX_PEERS];
+  int n;
+};
+
+__global__ void __launch_bounds__(CB)
+sh_colors_bwd_local_kernel(int degree, int K, int C, int N, const float* __restrict__ means,
+                           const float* __restrict__ coeffs, const float* __restrict__ viewmats,
+                           const int2* __restrict__ radii, const float4* __restrict__ v_colors4, int has_depth,
+                           char* __restrict__ region, float* __restrict__ v_means, float* __restrict__ v_depths) {
+  extern __shared__ float s_rows[];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * CB;
+  const int count = min(CB, N - n0);
+  const int row = K * 3, RS = row | 1;
+  rows_to_smem(s_rows, coeffs + (size_t)n0 * row, count, row, RS, t);
+  if (blockIdx.x == 0 && t < C) {
+    float cx, cy, cz;
+    camera_position(viewmats + t * 16, cx, cy, cz);
+    reinterpret_cast<float4*>(region)[t] = make_float4(cx, cy, cz, 1.f);
+  }
+  __syncthreads();
+  if (t >= count) return;
+  const int nb = (degree + 1) * (degree + 1);
+  const int n = n0 + t;
+  float4* vrgb = reinterpret_cast<float4*>(region + RS_PEER_HEADER_BYTES);
+  float vmx = 0.f, vmy = 0.f, vmz = 0.f;
+  const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
+  const float* cf = s_rows + t * RS;
+  for (int c = 0; c < C; ++c) {
+    const size_t e = (size_t)c * N + n;
+    const float4 vc = __ldg(v_colors4 + e);
+    if (has_depth) v_depths[e] = vc.w;
+    const int2 rad = __ldg(radii + e);
+    const bool live = rad.x > 0 && rad.y > 0;
+    float cx, cy, cz;
+    camera_position(viewmats + c * 16, cx, cy, cz);
+    const float x = mx - cx, y = my - cy, z = mz - cz;
+    const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+    const float ux = x * inv, uy = y * inv, uz = z * inv;
+    float basis[16], gq[16];
+    rs::sh_basis(degree, ux, uy, uz, basis);
+    float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if (q < nb) { r += basis[q] * cf[q * 3]; g += basis[q] * cf[q * 3 + 1]; b += basis[q] * cf[q * 3 + 2]; }
+    const float vr = (live && r + 0.5f >= 0.f) ? vc.x : 0.f, vg = (live && g + 0.5f >= 0.f) ? vc.y : 0.f,
+                vb = (live && b + 0.5f >= 0.f) ? vc.z : 0.f;
+    vrgb[e] = make_float4(vr, vg, vb, 0.f);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) gq[q] = q < nb ? vr * cf[q * 3] + vg * cf[q * 3 + 1] + vb * cf[q * 3 + 2] : 0.f;
+    float bx, by, bz;
+    rs::sh_basis_vjp(degree, ux, uy, uz, gq, bx, by, bz);
+    const float dd = ux * bx + uy * by + uz * bz;
+    vmx += (bx - ux * dd) * inv; vmy += (by - uy * dd) * inv; vmz += (bz - uz * dd) * inv;
+  }
+  v_means[n * 3] = vmx; v_means[n * 3 + 1] = vmy; v_means[n * 3 + 2] = vmz;
+}
+
+__global__ void __launch_bounds__(CB)
+sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ means, const PeerSources src,
+                        float* __restrict__ v_coeffs) {
+  extern __shared__ float s_rows[];
+  __shared__ float4 s_campos[64];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * CB;
+  const int count = min(CB, N - n0);
+  const int row = K * 3, RS = row | 1;
+  const int nb = (degree + 1) * (degree + 1);
+  float* o = s_rows + t * RS;
+  for (int i = 0; i < row; ++i) o[i] = 0.f;
+  const int n = n0 + t;
+  const bool active = t < count;
+  float mx = 0.f, my = 0.f, mz = 0.f;
+  if (active) { mx = __ldg(means + n * 3); my = __ldg(means + n * 3 + 1); mz = __ldg(means + n * 3 + 2); }
+  for (int g = 0; g < src.n; ++g) {
+    const int cams = src.cams[g];
+    __syncthreads();
+    if (t < cams) s_campos[t] = __ldcg(reinterpret_cast<const float4*>(src.base[g]) + t);
+    __syncthreads();
+    const float4* vrgb = reinterpret_cast<const float4*>(src.base[g] + RS_PEER_HEADER_BYTES);
+    for (int c0 = 0; c0 < cams; c0 += 4) {
+      float4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)   // independent (possibly remote) 16-byte loads in flight before any is consumed
+        v[i] = (active && c0 + i < cams) ? __ldcg(vrgb + (size_t)(c0 + i) * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (v[i].x == 0.f && v[i].y == 0.f && v[i].z == 0.f) continue;   // culled / clamped: exact zeros
+        const float4 cp = s_campos[c0 + i];
+        const float x = mx - cp.x, y = my - cp.y, z = mz - cp.z;
+        const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
+        float basis[16];
+        rs::sh_basis(degree, x * inv, y * inv, z * inv, basis);
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (q < nb) { o[q * 3] += basis[q] * v[i].x; o[q * 3 + 1] += basis[q] * v[i].y; o[q * 3 + 2] += basis[q] * v[i].z; }
+      }
+    }
+  }
+  __syncthreads();
+  smem_to_rows(s_rows, v_coeffs + (size_t)n0 * row, count, row, RS, t);
+}
+
 }  // namespace
 
 // colors4[C,N,4] = (max(SH(dir)+0.5, 0) rgb, depth or 0); coeffs[N,K,3] shared by all cameras; entries whose
@@ -201,5 +321,49 @@ extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* me
   sh_colors_bwd_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
       degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, (const float4*)v_colors4, has_depth, v_coeffs,
       v_means, v_depths);
+  RS_RETURN_LAST_ERROR();
+}
+
+// ---- camera-sharded split of rs_sh_colors_bwd (see the kernels above).  `region` is the caller's peer-visible
+// buffer of rs_sh_region_bytes(C, N) bytes; v_coeffs is NOT produced here but by rs_sh_coeffs_gather on every rank.
+extern "C" long long rs_sh_region_bytes(int C, int N) {
+  return (long long)RS_PEER_HEADER_BYTES + 16ll * (long long)(C > 0 ? C : 0) * (long long)(N > 0 ? N : 0);
+}
+
+extern "C" int rs_sh_colors_bwd_local(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                                      const float* viewmats, const int32_t* radii, const float* v_colors4,
+                                      int has_depth, void* region, float* v_means, float* v_depths, void* stream) {
+  RsSpan span__("rs_sh_colors_bwd_local", stream);
+  if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || C < 0 || N < 0) return RS_ERR_BAD_ARG;
+  if (C > RS_PEER_HEADER_BYTES / 16) return RS_ERR_UNSUPPORTED;
+  if (N == 0 || C == 0) return RS_OK;
+  if (!means || !coeffs || !viewmats || !radii || !v_colors4 || !region || !v_means || (has_depth && !v_depths))
+    return RS_ERR_BAD_ARG;
+  const size_t smem = sizeof(float) * CB * ((K * 3) | 1);
+  sh_colors_bwd_local_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(
+      degree, K, C, N, means, coeffs, viewmats, (const int2*)radii, (const float4*)v_colors4, has_depth, (char*)region,
+      v_means, v_depths);
+  RS_RETURN_LAST_ERROR();
+}
+
+// regions[n_sources]: device-visible base pointers (local, peer-mapped or all-gathered copies) of the regions the
+// ranks filled with rs_sh_colors_bwd_local, cams[n_sources]: cameras in each.  v_coeffs[N,K,3] is overwritten with
+// the sum over all sources, accumulated in source order.
+extern "C" int rs_sh_coeffs_gather(int degree, int K, int N, const float* means, const void* const* regions,
+                                   const int* cams, int n_sources, float* v_coeffs, void* stream) {
+  RsSpan span__("rs_sh_coeffs_gather", stream);
+  if (degree < 0 || degree > 3 || K < (degree + 1) * (degree + 1) || K > 16 || N < 0) return RS_ERR_BAD_ARG;
+  if (n_sources < 0 || n_sources > RS_MAX_PEERS) return RS_ERR_UNSUPPORTED;
+  if (N == 0) return RS_OK;
+  if (!means || !v_coeffs || (n_sources > 0 && (!regions || !cams))) return RS_ERR_BAD_ARG;
+  PeerSources src;
+  src.n = n_sources;
+  for (int g = 0; g < RS_MAX_PEERS; ++g) {
+    src.base[g] = g < n_sources ? (const char*)regions[g] : nullptr;
+    src.cams[g] = g < n_sources ? cams[g] : 0;
+    if (g < n_sources && (!regions[g] || cams[g] < 0 || cams[g] > RS_PEER_HEADER_BYTES / 16)) return RS_ERR_BAD_ARG;
+  }
+  const size_t smem = sizeof(float) * CB * ((K * 3) | 1);
+  sh_coeffs_gather_kernel<<<rs_div_up(N, CB), CB, smem, (cudaStream_t)stream>>>(degree, K, N, means, src, v_coeffs);
   RS_RETURN_LAST_ERROR();
 }

@@ -1,0 +1,100 @@
+// Peer-visible device memory for the camera-sharded multi-GPU step (one process per GPU): allocation, CUDA-IPC
+// export / import so that a kernel on rank r can read rank g's buffer over NVLink, and a flag handshake
+// (signal = remote store, wait = local spin) that orders "rank g has published step s" before "rank r reads it".
+// These are set-up / synchronisation entry points, not part of the single-GPU hot path: rs_peer_alloc and
+// rs_peer_import are the only functions of the library that allocate or map memory.
+#include "common.cuh"
+#include <string.h>
+
+namespace {
+
+__global__ void peer_signal_kernel(unsigned long long* const* flag_arrays, int n_ranks, int my_rank,
+                                   unsigned long long value) {
+  const int g = threadIdx.x;
+  if (g >= n_ranks) return;
+  __threadfence_system();   // everything this stream wrote before the signal is visible system-wide first
+  unsigned long long* dst = flag_arrays[g] + my_rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(value) : "memory");
+}
+
+// spins until flags[g] >= value for every g; gives up after ~timeout_ms and raises *timed_out instead of hanging
+__global__ void peer_wait_kernel(const unsigned long long* flags, int n_ranks, unsigned long long value,
+                                 long long timeout_cycles, int* timed_out) {
+  const int g = threadIdx.x;
+  if (g >= n_ranks) return;
+  const long long t0 = clock64();
+  unsigned long long v;
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + g) : "memory");
+    if (v >= value) return;
+    __nanosleep(200);
+  } while (clock64() - t0 < timeout_cycles);
+  *timed_out = 1;
+}
+
+}  // namespace
+
+extern "C" int rs_peer_alloc(long long bytes, void** ptr) {
+  if (bytes <= 0 || !ptr) return RS_ERR_BAD_ARG;
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaMemset(*ptr, 0, (size_t)bytes);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}
+
+extern "C" int rs_peer_free(void* ptr) {
+  if (!ptr) return RS_OK;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}
+
+extern "C" int rs_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int rs_peer_export(void* ptr, void* handle_out) {
+  if (!ptr || !handle_out) return RS_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  memcpy(handle_out, &h, sizeof(h));
+  return RS_OK;
+}
+
+extern "C" int rs_peer_import(const void* handle, void** ptr) {
+  if (!handle || !ptr) return RS_ERR_BAD_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}
+
+extern "C" int rs_peer_unimport(void* ptr) {
+  if (!ptr) return RS_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}
+
+// flag_arrays (DEVICE array of n_ranks pointers): rank g's flag array (u64[n_ranks]) as mapped in this process;
+// writes `value` into slot my_rank of every rank's array, after all earlier work of `stream`.
+extern "C" int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsigned long long value,
+                              void* stream) {
+  RsSpan span__("rs_peer_signal", stream);
+  if (!flag_arrays_dev || n_ranks <= 0 || n_ranks > 32 || my_rank < 0 || my_rank >= n_ranks) return RS_ERR_BAD_ARG;
+  peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long* const*)flag_arrays_dev, n_ranks, my_rank,
+                                                         value);
+  RS_RETURN_LAST_ERROR();
+}
+
+// blocks `stream` (on the device) until every slot of the LOCAL flag array is >= value; *timed_out_dev (device int,
+// zeroed by the caller) is raised instead of hanging if a peer does not arrive within timeout_ms.
+extern "C" int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long long value, int timeout_ms,
+                            int* timed_out_dev, void* stream) {
+  RsSpan span__("rs_peer_wait", stream);
+  if (!local_flags || n_ranks <= 0 || n_ranks > 32 || !timed_out_dev || timeout_ms <= 0) return RS_ERR_BAD_ARG;
+  const long long cycles = (long long)timeout_ms * 1900000ll;   // ~1.9 GHz SM clock
+  peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)local_flags, n_ranks, value, cycles,
+                                                       timed_out_dev);
+  RS_RETURN_LAST_ERROR();
+}

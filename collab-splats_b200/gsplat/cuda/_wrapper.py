@@ -26,6 +26,9 @@ TILE_SIZE = 16
 #   "presort": argsort the C*N depths once, emit the keys in depth order, radix-sort only the (camera|tile) bits
 #   "radix":   emit in (camera, Gaussian, tile) order, radix-sort all 32 + tile_bits + cam_bits key bits
 ISECT_SORT_METHOD = "presort"
+# Set by radegs_b200.multiview.ShGradExchange while a camera-sharded multi-GPU step runs: the backward of the
+# fused SH colours then publishes per-camera colour gradients instead of producing the coefficient gradient.
+SH_GRAD_SINK = None
 
 
 def _c(t: Optional[Tensor], dtype=torch.float32) -> Optional[Tensor]:
@@ -365,9 +368,21 @@ class _SHColors(torch.autograd.Function):
         means, coeffs, viewmats, radii = ctx.saved_tensors
         degree, has_depth = ctx.cfg
         C, N, K = viewmats.shape[0], means.shape[0], coeffs.shape[-2]
-        v_coeffs = torch.empty_like(coeffs)
         v_means = torch.empty_like(means)
         v_depths = torch.empty(C, N, device=means.device, dtype=torch.float32) if has_depth else None
+        sink = SH_GRAD_SINK
+        if sink is not None:
+            # camera-sharded multi-GPU step: publish the masked colour gradients; the coefficient gradient (summed
+            # over the cameras of ALL ranks) is rebuilt by sink.finish() -- see radegs_b200.multiview.ShGradExchange
+            with torch.cuda.device(means.device):
+                st = _be.stream_ptr(means.device)
+                _be.check(lib.rs_sh_colors_bwd_local(degree, K, C, N, _be.ptr(means), _be.ptr(coeffs),
+                                                     _be.ptr(viewmats), _be.ptr(radii), _be.ptr(_c(v_colors4)),
+                                                     int(has_depth), sink.local_region_ptr(C, N), _be.ptr(v_means),
+                                                     _be.ptr(v_depths), st), "rs_sh_colors_bwd_local")
+                sink.published(means, degree, K, st)
+            return None, v_means, None, None, None, v_depths
+        v_coeffs = torch.empty_like(coeffs)
         with torch.cuda.device(means.device):
             _be.check(lib.rs_sh_colors_bwd(degree, K, C, N, _be.ptr(means), _be.ptr(coeffs), _be.ptr(viewmats),
                                            _be.ptr(radii), _be.ptr(_c(v_colors4)), int(has_depth), _be.ptr(v_coeffs),

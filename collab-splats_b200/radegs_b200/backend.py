@@ -65,6 +65,17 @@ _SIGNATURES = {
     "rs_sh_colors_fwd": (_i, [_i, _i, _i, _i] + [_p] * 6 + [_p]),
     "rs_sh_colors_bwd": (_i, [_i, _i, _i, _i] + [_p] * 5 + [_i] + [_p] * 3 + [_p]),
     "rs_unpack_colors_grad": (_i, [_p, _ll, _i, _i, _p, _p]),
+    "rs_sh_region_bytes": (_ll, [_i, _i]),
+    "rs_sh_colors_bwd_local": (_i, [_i, _i, _i, _i] + [_p] * 5 + [_i] + [_p] * 3 + [_p]),
+    "rs_sh_coeffs_gather": (_i, [_i, _i, _i, _p, _p, _p, _i, _p, _p]),
+    "rs_peer_alloc": (_i, [_ll, _p]),
+    "rs_peer_free": (_i, [_p]),
+    "rs_peer_handle_bytes": (_i, []),
+    "rs_peer_export": (_i, [_p, _p]),
+    "rs_peer_import": (_i, [_p, _p]),
+    "rs_peer_unimport": (_i, [_p]),
+    "rs_peer_signal": (_i, [_p, _i, _i, C.c_ulonglong, _p]),
+    "rs_peer_wait": (_i, [_p, _i, C.c_ulonglong, _i, _p, _p]),
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 

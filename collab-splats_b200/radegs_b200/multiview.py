@@ -84,3 +84,184 @@ def global_batch_loss_scale(n_views: int) -> float:
     """Each rank averages the loss over the whole batch so that the summed gradient equals the gradient of the
     mean loss over all views of the step."""
     return 1.0 / float(n_views)
+
+
+class ShGradExchange:
+    """SH-coefficient gradients for the camera-sharded step WITHOUT all-reducing them (csrc/colors.cu, csrc/peer.cu).
+
+    The coefficient gradient of one camera is the outer product ``Y_k(dir(n, camera)) x v_rgb[n]``: 48 floats per
+    Gaussian that carry 3.  Each rank therefore publishes its clamp/visibility-masked colour gradients (16 B per
+    Gaussian and camera) and every rank rebuilds the sum over the cameras of ALL ranks with one kernel
+    (``rs_sh_coeffs_gather``), in a fixed (rank, camera) order, so all replicas hold bit-identical gradients.  At sh3
+    this replaces a 192 B/Gaussian all-reduce (ring traffic 2(G-1)/G x 192 B) by (G-1) x 16 B/Gaussian of reads.
+
+    ``mode="p2p"``: the regions live in CUDA-IPC-shared device memory and the gather kernel reads the other ranks'
+    rows directly over NVLink; a flag handshake (remote store / local spin, ``rs_peer_signal`` / ``rs_peer_wait``)
+    orders publication before consumption, and two regions alternate so a rank may start its next backward while a
+    slower peer still reads the previous one.  ``mode="allgather"``: the regions are ordinary tensors, all-gathered
+    with ``torch.distributed`` (NCCL, or gloo-free single process), then the same kernel reads the local copy.
+
+    Usage per step::
+
+        ex.begin_step()
+        with ex:                      # routes the backward of the fused SH colours to rs_sh_colors_bwd_local
+            loss.backward()
+        params["sh_coeffs"].grad = ex.finish()
+    """
+
+    def __init__(self, n_gaussians: int, cams_per_rank: int, device, group=None, mode: str = "p2p",
+                 timeout_ms: int = 5000):
+        from radegs_b200 import backend as be
+        import ctypes
+        self.be, self.ct = be, ctypes
+        self.lib = be.load()
+        self.N, self.C = int(n_gaussians), int(cams_per_rank)
+        self.device = torch.device(device)
+        self.group = group
+        self.timeout_ms = int(timeout_ms)
+        ready = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ready else 1
+        self.rank = dist.get_rank(group) if ready else 0
+        if self.world > 16:
+            raise NotImplementedError("ShGradExchange supports up to 16 ranks (one NVSwitch domain)")
+        self.region_bytes = int(self.lib.rs_sh_region_bytes(self.C, self.N))
+        self.region_stride = (self.region_bytes + 255) // 256 * 256
+        self.step = 0
+        self._pending = None
+        self.mode = mode
+        self._peer_ptrs = []        # imported mappings, closed in close()
+        self._own = []              # own cudaMalloc'ed blocks
+        cams = [self.C] * self.world
+        if ready and self.world > 1:
+            got = [None] * self.world
+            dist.all_gather_object(got, self.C, group=group)
+            cams = [int(c) for c in got]
+        self.cams = cams
+        with torch.cuda.device(self.device):
+            if mode == "p2p":
+                self._init_p2p()
+            elif mode == "allgather":
+                if len(set(cams)) != 1:
+                    raise NotImplementedError("allgather mode needs the same number of cameras on every rank")
+                self.local = torch.zeros(2, self.region_stride, device=self.device, dtype=torch.uint8)
+                self.gathered = torch.zeros(self.world, self.region_stride, device=self.device, dtype=torch.uint8)
+            else:
+                raise ValueError(mode)
+            self.timed_out = torch.zeros(1, device=self.device, dtype=torch.int32)
+
+    # ---- set-up: allocate, export, exchange handles, import
+    def _alloc(self, nbytes: int) -> int:
+        p = self.ct.c_void_p()
+        self.be.check(self.lib.rs_peer_alloc(nbytes, self.ct.byref(p)), "rs_peer_alloc")
+        self._own.append(p.value)
+        return p.value
+
+    def _init_p2p(self):
+        ct, lib, be = self.ct, self.lib, self.be
+        regions = self._alloc(2 * self.region_stride)         # two alternating regions
+        flags = self._alloc(256)                               # u64[world], written by the peers
+        hb = lib.rs_peer_handle_bytes()
+        handles = []
+        for ptr in (regions, flags):
+            buf = ct.create_string_buffer(hb)
+            be.check(lib.rs_peer_export(ct.c_void_p(ptr), buf), "rs_peer_export")
+            handles.append(bytes(buf.raw))
+        everyone = [handles]
+        if self.world > 1:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, handles, group=self.group)
+        self.region_base, self.flag_base = [], []
+        for g, (h_reg, h_flag) in enumerate(everyone):
+            if g == self.rank:
+                self.region_base.append(regions)
+                self.flag_base.append(flags)
+                continue
+            mapped = []
+            for h in (h_reg, h_flag):
+                p = ct.c_void_p()
+                be.check(lib.rs_peer_import(ct.create_string_buffer(h, hb), ct.byref(p)), "rs_peer_import")
+                self._peer_ptrs.append(p.value)
+                mapped.append(p.value)
+            self.region_base.append(mapped[0])
+            self.flag_base.append(mapped[1])
+        self.flag_ptrs_dev = torch.tensor(self.flag_base, dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)                     # every mapping exists before anyone signals
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_available() and dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)                     # nobody still reads a region that is about to go
+        for p in self._peer_ptrs:
+            self.lib.rs_peer_unimport(self.ct.c_void_p(p))
+        for p in self._own:
+            self.lib.rs_peer_free(self.ct.c_void_p(p))
+        self._peer_ptrs, self._own = [], []
+
+    # ---- per step
+    def begin_step(self):
+        self.step += 1
+        self._pending = None
+
+    def __enter__(self):
+        import gsplat.cuda._wrapper as wr
+        self._prev_sink, wr.SH_GRAD_SINK = wr.SH_GRAD_SINK, self
+        return self
+
+    def __exit__(self, *exc):
+        import gsplat.cuda._wrapper as wr
+        wr.SH_GRAD_SINK = self._prev_sink
+
+    def _parity(self) -> int:
+        return self.step & 1
+
+    def local_region_ptr(self, C: int, N: int):
+        """Called by the SH-colour backward: where this rank's rows of the current step go."""
+        if (C, N) != (self.C, self.N):
+            raise RuntimeError(f"ShGradExchange was built for {self.C} cameras x {self.N} Gaussians, got {C} x {N}")
+        if self._pending is not None:
+            raise RuntimeError("one fused SH-colour backward per step (call begin_step() before the next one)")
+        if self.mode == "p2p":
+            return self.ct.c_void_p(self.region_base[self.rank] + self._parity() * self.region_stride)
+        return self.be.ptr(self.local[self._parity()])
+
+    def published(self, means: Tensor, degree: int, K: int, stream_ptr):
+        """Called right after rs_sh_colors_bwd_local was queued: tell the peers (p2p) and remember the inputs."""
+        self._pending = (means, int(degree), int(K))
+        if self.mode == "p2p":
+            self.be.check(self.lib.rs_peer_signal(self.be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step,
+                                                  stream_ptr), "rs_peer_signal")
+
+    @torch.no_grad()
+    def finish(self, out: Optional[Tensor] = None) -> Tensor:
+        """-> d loss / d sh_coeffs [N,K,3] summed over the cameras of all ranks (identical on every rank)."""
+        if self._pending is None:
+            raise RuntimeError("finish() without a backward through the fused SH colours in this step")
+        means, degree, K = self._pending
+        ct, lib, be = self.ct, self.lib, self.be
+        if out is None:
+            out = torch.empty(self.N, K, 3, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            st = be.stream_ptr(self.device)
+            if self.mode == "p2p":
+                be.check(lib.rs_peer_wait(ct.c_void_p(self.flag_base[self.rank]), self.world, self.step,
+                                          self.timeout_ms, be.ptr(self.timed_out), st), "rs_peer_wait")
+                bases = [b + self._parity() * self.region_stride for b in self.region_base]
+            else:
+                if self.world > 1:
+                    dist.all_gather_into_tensor(self.gathered.view(-1), self.local[self._parity()], group=self.group)
+                else:
+                    self.gathered[0].copy_(self.local[self._parity()])
+                base = self.gathered.data_ptr()
+                bases = [base + g * self.region_stride for g in range(self.world)]
+            regions = (ct.c_void_p * self.world)(*bases)
+            cams = (ct.c_int * self.world)(*self.cams)
+            be.check(lib.rs_sh_coeffs_gather(degree, K, self.N, be.ptr(means), regions, cams, self.world, be.ptr(out),
+                                             st), "rs_sh_coeffs_gather")
+        self._pending = None
+        return out
+
+    def check(self):
+        """Raises if a peer failed to publish within the timeout (one device->host read: call it off the hot path)."""
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError("ShGradExchange: a peer rank did not publish its colour gradients in time")

@@ -187,6 +187,34 @@ int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* means, const 
                      const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,
                      float* v_coeffs, float* v_means, float* v_depths /* NULL unless has_depth */, void* stream);
 
+/* ---- camera-sharded multi-GPU form of rs_sh_colors_bwd (Gaussians replicated, cameras sharded).
+ * The SH-coefficient gradient of one camera is Y_k(dir) x v_rgb (48 floats carrying 3), so instead of all-reducing
+ * 192 B per Gaussian each rank publishes its masked colour gradients (16 B per Gaussian and camera) in a
+ * peer-visible `region` and every rank rebuilds the sum over ALL cameras of ALL ranks itself, reading the other
+ * ranks' regions over NVLink (regions[] = peer-mapped pointers) or from an all-gathered copy.
+ * region layout: [1024 B header: float4 camera position per camera][float4 vrgb[C][N]], rs_sh_region_bytes(C, N). */
+long long rs_sh_region_bytes(int C, int N);
+int rs_sh_colors_bwd_local(int degree, int K, int C, int N, const float* means, const float* coeffs,
+                           const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,
+                           void* region, float* v_means, float* v_depths /* NULL unless has_depth */, void* stream);
+int rs_sh_coeffs_gather(int degree, int K, int N, const float* means, const void* const* regions /* host array */,
+                        const int* cams /* host array */, int n_sources /* <= 16 */, float* v_coeffs, void* stream);
+
+/* ---- peer-visible memory + flag handshake for the above (one process per GPU, CUDA IPC).  rs_peer_alloc /
+ * rs_peer_import are the only entry points of the library that allocate or map memory (set-up time only).
+ * rs_peer_signal stores `value` into slot my_rank of every rank's flag array (u64[n_ranks]) after all earlier work
+ * of `stream`; rs_peer_wait blocks `stream` on the device until every slot of the local array is >= value and
+ * raises *timed_out_dev instead of hanging when a peer does not arrive within timeout_ms. */
+int rs_peer_alloc(long long bytes, void** ptr);
+int rs_peer_free(void* ptr);
+int rs_peer_handle_bytes(void);
+int rs_peer_export(void* ptr, void* handle_out);
+int rs_peer_import(const void* handle, void** ptr);
+int rs_peer_unimport(void* ptr);
+int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsigned long long value, void* stream);
+int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long long value, int timeout_ms, int* timed_out_dev,
+                 void* stream);
+
 /* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
  * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and
  * collab_splats/models/rade_gs_model.py:202-219,292-307 as run by the training step.

@@ -580,6 +580,93 @@ def test_sh_colors_fused(cuda_dev, degree, with_depth, views):
         assert ok, msg
 
 
+@pytest.mark.parametrize("degree,cams", [(3, [1, 2, 1]), (1, [2, 2]), (0, [1]), (3, [1] * 8)])
+def test_sh_gradient_split_over_virtual_ranks(cuda_dev, degree, cams):
+    """Camera-sharded form of the SH backward (csrc/colors.cu: rs_sh_colors_bwd_local on every 'rank', then
+    rs_sh_coeffs_gather over all regions) against the oracle's autograd over ALL cameras at once: the coefficient
+    gradient rebuilt from the published colour gradients equals the sum the all-reduce would have produced."""
+    import ctypes as ct
+    from radegs_b200 import backend as be
+    lib = be.load()
+    views = sum(cams)
+    cfg, gs, vm, Ks = small_scene(n=5000, views=views, spread=1.8)
+    means, quats, scales, _, sh = scenes.activate(gs, 3)
+    sh = sh * 6.0
+    radii, _, depths = O.fully_fused_projection(means, quats, scales, vm, Ks, cfg.width, cfg.height)[:3]
+    N, K = means.shape[0], sh.shape[1]
+    mc, sc = means.clone().requires_grad_(True), sh.clone().requires_grad_(True)
+    campos = torch.linalg.inv(vm)[:, :3, 3]
+    ref = O.spherical_harmonics(degree, mc[None] - campos[:, None], sc[None].expand(views, -1, -1, -1),
+                                masks=(radii > 0).all(-1))
+    ref = torch.clamp_min(ref + 0.5, 0.0)
+    w = torch.randn(views, N, 4, generator=torch.Generator().manual_seed(4))
+    (ref * w[..., :3]).sum().backward()
+    md, sd = means.to(cuda_dev), sh.to(cuda_dev).contiguous()
+    st = be.stream_ptr(cuda_dev)
+    regions, v_means_sum, c0 = [], torch.zeros(N, 3, device=cuda_dev), 0
+    for C in cams:
+        region = torch.zeros(lib.rs_sh_region_bytes(C, N), device=cuda_dev, dtype=torch.uint8)
+        v_means = torch.empty(N, 3, device=cuda_dev)
+        v_depths = torch.empty(C, N, device=cuda_dev)
+        vm_g, radii_g = vm[c0:c0 + C].to(cuda_dev).contiguous(), radii[c0:c0 + C].to(cuda_dev).contiguous()
+        w_g = w[c0:c0 + C].to(cuda_dev).contiguous()       # named: the pointers must outlive the launch
+        be.check(lib.rs_sh_colors_bwd_local(degree, K, C, N, be.ptr(md), be.ptr(sd), be.ptr(vm_g), be.ptr(radii_g),
+                                            be.ptr(w_g), 1, be.ptr(region), be.ptr(v_means), be.ptr(v_depths), st),
+                 "local")
+        assert torch.equal(v_depths.cpu(), w[c0:c0 + C, :, 3])
+        v_means_sum += v_means
+        regions.append(region)
+        c0 += C
+    v_coeffs = torch.full((N, K, 3), float("nan"), device=cuda_dev)
+    ptrs = (ct.c_void_p * len(cams))(*[r.data_ptr() for r in regions])
+    be.check(lib.rs_sh_coeffs_gather(degree, K, N, be.ptr(md), ptrs, (ct.c_int * len(cams))(*cams), len(cams),
+                                     be.ptr(v_coeffs), st), "gather")
+    ok, msg = grad_close_report("v_coeffs (gathered)", v_coeffs, sc.grad, rel=1e-4)
+    assert ok, msg
+    ok, msg = grad_close_report("v_means (sum of the local parts)", v_means_sum, mc.grad, rel=2e-3)
+    assert ok, msg
+    nb = (degree + 1) ** 2
+    assert bool((v_coeffs[:, nb:] == 0).all()), "bands above the active degree get exact zeros"
+
+
+@pytest.mark.parametrize("mode", ["p2p", "allgather"])
+def test_sh_grad_exchange_single_process(cuda_dev, mode):
+    """ShGradExchange with one rank (signal to self / local gather) through the full rasterization() backward:
+    same gradients as the plain path, on two consecutive steps (alternating regions)."""
+    from gsplat.rendering import rasterization
+    from radegs_b200.multiview import ShGradExchange
+    cfg, gs, vm, Ks = small_scene(n=3000, w=96, h=64, views=2)
+    params = scenes.activate(gs, 3)
+
+    def run(exchange):
+        leaves = [p.detach().to(cuda_dev).requires_grad_(True) for p in params]
+        out = rasterization(*leaves, vm.to(cuda_dev), Ks.to(cuda_dev), cfg.width, cfg.height, sh_degree=3, packed=False,
+                            render_mode="RGB+ED", rasterize_mode="antialiased", return_depth_normal=True)
+        g = torch.Generator().manual_seed(0)
+        loss = sum((o * torch.randn(o.shape, generator=g).to(cuda_dev)).sum() for o in out[:5])
+        if exchange is None:
+            loss.backward()
+        else:
+            exchange.begin_step()
+            with exchange:
+                loss.backward()
+            assert leaves[4].grad is None
+            leaves[4].grad = exchange.finish()
+        return [l.grad.clone() for l in leaves]
+
+    ref = run(None)
+    ex = ShGradExchange(3000, 2, cuda_dev, mode=mode)
+    try:
+        for _ in range(3):
+            got = run(ex)
+            for a, b, nm in zip(got, ref, ["means", "quats", "scales", "opacities", "sh"]):
+                ok, msg = grad_close_report("v_" + nm, a, b, rel=1e-5)
+                assert ok, msg
+        ex.check()
+    finally:
+        ex.close()
+
+
 @pytest.mark.parametrize("cfg_id", [2, 3])
 def test_full_size_adjoint_identity(cuda_dev, cfg_id):
     """BASELINE config 2 (1M, 1080p, D=3) and config 3 (500k, 960x540, 3+64 feature channels) at full size.
