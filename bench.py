@@ -159,7 +159,7 @@ class Workload:
     def step_resident(self):
         self.zero_grad()
         loss = self.forward_loss(self.viewmat, self.K, self.gt)
-        loss.backward()
+        self.backward(loss)
         return loss
 
     # ---- end-to-end step: host inputs -> device every step, loss -> host every step, software-pipelined the way a
@@ -193,7 +193,7 @@ class Workload:
         self._prefetch((i + 1) & 1)                      # next step's H2D overlaps this step's kernels
         self.zero_grad()
         loss = self.forward_loss(b["vm"], b["K"], b["gt"])
-        loss.backward()
+        self.backward(loss)
         return loss
 
     def read_loss_async(self, loss):
@@ -209,29 +209,59 @@ class Workload:
         prev.synchronize()
         return float(self.loss_host[(i + 1) & 1][0])
 
-    # ---- multi-GPU: Gaussian-gradient all-reduce.  The SH coefficients are 192 of the 236 B per Gaussian and their
-    # gradient is final as soon as the colour backward has run, so its all-reduce is launched from a gradient hook
-    # (async, NCCL stream) and overlaps the projection backward; the remaining small gradients go in one flat bucket.
-    def enable_overlapped_allreduce(self):
+    # ---- multi-GPU gradient exchange.  The SH coefficients are 192 of the 236 B of gradient per Gaussian, and one
+    # camera's coefficient gradient is an outer product Y_k(dir) x v_rgb, so they are NOT all-reduced: every rank
+    # publishes its masked colour gradients (16 B per Gaussian) and rebuilds the sum over all ranks' cameras with one
+    # kernel that reads the peers over NVLink (radegs_b200.multiview.ShGradExchange, csrc/colors.cu + peer.cu).  The
+    # remaining 44 B per Gaussian go through one NCCL all-reduce that overlaps that kernel.
+    def enable_grad_exchange(self, mode: str):
         import torch.distributed as dist
-        self.pending = []
+        from radegs_b200.multiview import ShGradExchange
+        self.exchange, self.exchange_mode = None, mode
         self.collectives_on = True
-        big = self.params["sh_coeffs"]
+        if mode in ("p2p", "allgather"):
+            try:
+                self.exchange = ShGradExchange(self.cfg.n_gaussians, 1, self.device, mode=mode)
+            except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container)
+                print(f"ShGradExchange({mode}) unavailable: {e}; falling back to all-reduce", file=sys.stderr)
+                self.exchange_mode = "allreduce"
+        ok = torch.tensor([1 if self.exchange is not None else 0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)           # all ranks must agree on the scheme
+        if int(ok.item()) == 0 and self.exchange is not None:
+            self.exchange.close()
+            self.exchange, self.exchange_mode = None, "allreduce"
+        if self.exchange is None:
+            self.exchange_mode = "allreduce"
+            self.pending = []
+            big = self.params["sh_coeffs"]
 
-        def hook(param):
-            if self.collectives_on:          # switched off for the rank-0-only per-kernel timing steps
-                self.pending.append(dist.all_reduce(param.grad, async_op=True))
-        big.register_post_accumulate_grad_hook(hook)
+            def hook(param):
+                if self.collectives_on:      # switched off for the rank-0-only per-kernel timing steps
+                    self.pending.append(dist.all_reduce(param.grad, async_op=True))
+            big.register_post_accumulate_grad_hook(hook)
+
+    def backward(self, loss):
+        ex = getattr(self, "exchange", None)
+        if ex is None or not self.collectives_on:
+            loss.backward()
+            return
+        ex.begin_step()
+        with ex:
+            loss.backward()
 
     def allreduce_grads(self):
         import torch.distributed as dist
-        small = [v.grad.reshape(-1) for k, v in self.params.items() if k != "sh_coeffs" or not hasattr(self, "pending")]
+        ex = getattr(self, "exchange", None)
+        small = [v.grad.reshape(-1) for k, v in self.params.items() if k != "sh_coeffs"]
         flat = torch.cat(small)
-        dist.all_reduce(flat)
-        if hasattr(self, "pending"):
+        work = dist.all_reduce(flat, async_op=True)          # NCCL stream: overlaps the gather kernel below
+        if ex is not None:
+            self.params["sh_coeffs"].grad = ex.finish()
+        else:
             for w in self.pending:
                 w.wait()
             self.pending.clear()
+        work.wait()
         return flat
 
 
@@ -410,6 +440,8 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-loss", action="store_true", help="use the unfused torch loss glue (for comparison)")
+    ap.add_argument("--grad-exchange", default="p2p", choices=["p2p", "allgather", "allreduce"],
+                    help="N > 1: how the SH-coefficient gradients are combined (default: peer-to-peer gather kernel)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE resident step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
@@ -447,7 +479,7 @@ def main():
     wl = Workload(args.config, device, rank, world)
     wl.fused_loss = not args.torch_loss
     if world > 1:
-        wl.enable_overlapped_allreduce()
+        wl.enable_grad_exchange(args.grad_exchange)
 
     def resident():
         wl.step_resident()
@@ -488,7 +520,8 @@ def main():
                                f"1 view {wl.cfg.width}x{wl.cfg.height} per GPU per step, RGB+ED antialiased, "
                                "fwd + L1 + depth-normal loss + bwd",
                    "views_per_step": world, "parallelism": f"camera-sharded x{world}, Gaussians replicated"
-                                                             + (", NCCL allreduce of parameter grads" if world > 1 else ""),
+                                                             + (f", SH-coefficient grads via {wl.exchange_mode} exchange, "
+                                                                "other parameter grads via NCCL allreduce" if world > 1 else ""),
                    "l2": "inputs exceed L2 (236 MB of SH coefficients + per-step intersection buffers > 126 MB)",
                    "optimizer": "none (hot path only)",
                    "e2e_pipeline": "next step's H2D on a copy stream; loss D2H read one step later (pinned)", "n_isects": int(wl.last_meta["flatten_ids"].numel())},
@@ -531,6 +564,9 @@ def main():
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
+        if getattr(wl, "exchange", None) is not None:
+            wl.exchange.check()
+            wl.exchange.close()
         dist.barrier()
         dist.destroy_process_group()
 
