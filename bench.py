@@ -511,6 +511,37 @@ def main():
         ms_e2e = time_region(e2e, args.steps, world, device)
     value = world * args.steps / (ms / 1000.0)
     value_e2e = world * args.steps / (ms_e2e / 1000.0)
+    multi = None
+    if world > 1:
+        # diagnostics (untimed): per-rank compute-only step time (no collectives: load imbalance between views shows
+        # here) and the exchange kernels' spans inside real steps on rank 0
+        import torch.distributed as dist
+        wl.collectives_on = False
+        wl.step_resident()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            wl.step_resident()
+        e1.record()
+        torch.cuda.synchronize(device)
+        wl.collectives_on = True
+        mine = torch.tensor([e0.elapsed_time(e1) / 5, float(wl.last_meta["flatten_ids"].numel())], device=device)
+        everyone = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)
+        lib.rs_timing_enable(1)
+        for _ in range(5):
+            resident()
+        torch.cuda.synchronize(device)
+        spans = backend.timing_collect()
+        lib.rs_timing_enable(0)
+        keys = ("rs_sh_colors_bwd_local", "rs_peer_signal", "rs_peer_wait", "rs_sh_coeffs_gather", "rs_sh_colors_bwd")
+        multi = {"compute_only_ms_per_rank": [round(float(v[0]), 4) for v in everyone],
+                 "n_isects_per_rank": [int(v[1]) for v in everyone],
+                 "exchange_spans_ms_rank0": {k: round(spans[k][0] / 5, 4) for k in keys if k in spans},
+                 "grad_exchange": wl.exchange_mode,
+                 "note": "step time = slowest rank's compute + exposed exchange; rs_peer_wait is time spent waiting "
+                         "for the slowest peer's colour gradients"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -530,6 +561,8 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
     }
+    if multi is not None:
+        line["multi_gpu"] = multi
     if rank == 0:
         # per-kernel device time measured INSIDE real steps (same inputs, same cache state): the library
         # brackets every entry point with CUDA events on the launching stream

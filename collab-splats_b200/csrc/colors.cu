@@ -180,6 +180,7 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
 // A source region is [header: RS_PEER_HEADER_BYTES, float4 campos per camera][float4 vrgb[cams][N]].
 constexpr int RS_PEER_HEADER_BYTES = 1024;  // up to 64 cameras per rank
 constexpr int RS_MAX_PEERS = 16;
+constexpr int RS_MAX_SOURCES = 64;   // cameras of all ranks in one step
 
 struct PeerSources {
   const char* base[RS_MAX_PEERS];
@@ -245,33 +246,45 @@ __global__ void __launch_bounds__(CB)
 sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ means, const PeerSources src,
                         float* __restrict__ v_coeffs) {
   extern __shared__ float s_rows[];
-  __shared__ float4 s_campos[64];
+  __shared__ float4 s_campos[RS_MAX_SOURCES];
+  __shared__ const float4* s_rowptr[RS_MAX_SOURCES];
+  __shared__ int s_total;
   const int t = threadIdx.x;
   const int n0 = blockIdx.x * CB;
   const int count = min(CB, N - n0);
   const int row = K * 3, RS = row | 1;
   const int nb = (degree + 1) * (degree + 1);
+  // flat list of sources (rank g, camera c), in (g, c) order: camera position + base of its vrgb rows
+  if (t == 0) {
+    int k = 0;
+    for (int g = 0; g < src.n; ++g)
+      for (int c = 0; c < src.cams[g] && k < RS_MAX_SOURCES; ++c, ++k)
+        s_rowptr[k] = reinterpret_cast<const float4*>(src.base[g] + RS_PEER_HEADER_BYTES) + (size_t)c * N;
+    s_total = k;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (t < total) {
+    int k = t, g = 0;
+    while (k >= src.cams[g]) { k -= src.cams[g]; ++g; }
+    s_campos[t] = __ldcg(reinterpret_cast<const float4*>(src.base[g]) + k);
+  }
   float* o = s_rows + t * RS;
   for (int i = 0; i < row; ++i) o[i] = 0.f;
+  __syncthreads();
   const int n = n0 + t;
-  const bool active = t < count;
-  float mx = 0.f, my = 0.f, mz = 0.f;
-  if (active) { mx = __ldg(means + n * 3); my = __ldg(means + n * 3 + 1); mz = __ldg(means + n * 3 + 2); }
-  for (int g = 0; g < src.n; ++g) {
-    const int cams = src.cams[g];
-    __syncthreads();
-    if (t < cams) s_campos[t] = __ldcg(reinterpret_cast<const float4*>(src.base[g]) + t);
-    __syncthreads();
-    const float4* vrgb = reinterpret_cast<const float4*>(src.base[g] + RS_PEER_HEADER_BYTES);
-    for (int c0 = 0; c0 < cams; c0 += 4) {
-      float4 v[4];
+  if (t < count) {
+    const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
+    constexpr int W = 8;   // (possibly remote) 16-byte loads in flight per thread before any is consumed
+    for (int k0 = 0; k0 < total; k0 += W) {
+      float4 v[W];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)   // independent (possibly remote) 16-byte loads in flight before any is consumed
-        v[i] = (active && c0 + i < cams) ? __ldcg(vrgb + (size_t)(c0 + i) * N + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < W; ++i)
+        v[i] = (k0 + i < total) ? __ldcg(s_rowptr[k0 + i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < W; ++i) {
         if (v[i].x == 0.f && v[i].y == 0.f && v[i].z == 0.f) continue;   // culled / clamped: exact zeros
-        const float4 cp = s_campos[c0 + i];
+        const float4 cp = s_campos[k0 + i];
         const float x = mx - cp.x, y = my - cp.y, z = mz - cp.z;
         const float inv = 1.f / fmaxf(sqrtf(x * x + y * y + z * z), 1e-12f);
         float basis[16];
@@ -358,6 +371,9 @@ extern "C" int rs_sh_coeffs_gather(int degree, int K, int N, const float* means,
   if (!means || !v_coeffs || (n_sources > 0 && (!regions || !cams))) return RS_ERR_BAD_ARG;
   PeerSources src;
   src.n = n_sources;
+  long long total_cams = 0;
+  for (int g = 0; g < n_sources; ++g) total_cams += cams[g] > 0 ? cams[g] : 0;
+  if (total_cams > RS_MAX_SOURCES || total_cams > CB) return RS_ERR_UNSUPPORTED;
   for (int g = 0; g < RS_MAX_PEERS; ++g) {
     src.base[g] = g < n_sources ? (const char*)regions[g] : nullptr;
     src.cams[g] = g < n_sources ? cams[g] : 0;

@@ -128,6 +128,7 @@ class ShGradExchange:
         self.region_stride = (self.region_bytes + 255) // 256 * 256
         self.step = 0
         self._pending = None
+        self._out = None
         self.mode = mode
         self._peer_ptrs = []        # imported mappings, closed in close()
         self._own = []              # own cudaMalloc'ed blocks
@@ -226,21 +227,29 @@ class ShGradExchange:
         return self.be.ptr(self.local[self._parity()])
 
     def published(self, means: Tensor, degree: int, K: int, stream_ptr):
-        """Called right after rs_sh_colors_bwd_local was queued: tell the peers (p2p) and remember the inputs."""
+        """Called right after rs_sh_colors_bwd_local was queued: tell the peers (p2p) and remember the inputs.
+        (Queuing the wait + gather kernels here on a side stream, to overlap the projection VJP, was measured SLOWER
+        at N=2 -- 2.66 vs 2.58 ms/step: that kernel fills the register file, so the two only take turns.)"""
         self._pending = (means, int(degree), int(K))
         if self.mode == "p2p":
             self.be.check(self.lib.rs_peer_signal(self.be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step,
                                                   stream_ptr), "rs_peer_signal")
 
+    def _out_buffer(self, K: int) -> Tensor:
+        """Two persistent result buffers alternate (the previous step's gradient stays valid for one more step)."""
+        if self._out is None or self._out[0].shape[1] != K:
+            self._out = [torch.empty(self.N, K, 3, device=self.device, dtype=torch.float32) for _ in range(2)]
+        return self._out[self._parity()]
+
     @torch.no_grad()
-    def finish(self, out: Optional[Tensor] = None) -> Tensor:
-        """-> d loss / d sh_coeffs [N,K,3] summed over the cameras of all ranks (identical on every rank)."""
+    def finish(self) -> Tensor:
+        """-> d loss / d sh_coeffs [N,K,3] summed over the cameras of all ranks (identical on every rank).  The
+        returned tensor is one of two buffers owned by the exchange: it stays valid until the step after next."""
         if self._pending is None:
             raise RuntimeError("finish() without a backward through the fused SH colours in this step")
         means, degree, K = self._pending
         ct, lib, be = self.ct, self.lib, self.be
-        if out is None:
-            out = torch.empty(self.N, K, 3, device=self.device, dtype=torch.float32)
+        out = self._out_buffer(K)
         with torch.cuda.device(self.device):
             st = be.stream_ptr(self.device)
             if self.mode == "p2p":

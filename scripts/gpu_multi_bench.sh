@@ -2,7 +2,7 @@
 # bench at N=$NG with the three SH-gradient exchange schemes (p2p gather kernel, all-gather + kernel, all-reduce)
 mkdir -p gpurun_out
 NG=${NG:-2}
-for mode in p2p allgather allreduce; do
+for mode in ${MODES:-p2p allgather allreduce}; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $NG --steps 20 --warmup 3 --grad-exchange $mode > gpurun_out/bench_n${NG}_$mode.json 2> gpurun_out/bench_n${NG}_$mode.err; echo "bench N=$NG $mode exit $?"
   tail -n 2 gpurun_out/bench_n${NG}_$mode.err | cut -c1-300
 done
