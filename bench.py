@@ -219,7 +219,7 @@ class Workload:
         from radegs_b200.multiview import ShGradExchange
         self.exchange, self.exchange_mode = None, mode
         self.collectives_on = True
-        if mode in ("p2p", "allgather"):
+        if mode in ("push", "p2p", "allgather"):
             try:
                 self.exchange = ShGradExchange(self.cfg.n_gaussians, 1, self.device, mode=mode)
             except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container)
@@ -440,8 +440,9 @@ def main():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--torch-loss", action="store_true", help="use the unfused torch loss glue (for comparison)")
-    ap.add_argument("--grad-exchange", default="p2p", choices=["p2p", "allgather", "allreduce"],
-                    help="N > 1: how the SH-coefficient gradients are combined (default: peer-to-peer gather kernel)")
+    ap.add_argument("--grad-exchange", default="push", choices=["push", "p2p", "allgather", "allreduce"],
+                    help="N > 1: how the SH-coefficient gradients are combined (default: copy-engine push into peer "
+                         "inboxes + local gather kernel; p2p = gather kernel pulls over NVLink)")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE resident step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()

@@ -76,6 +76,16 @@ extern "C" int rs_peer_unimport(void* ptr) {
   return RS_OK;
 }
 
+// device-to-device copy between peer-visible buffers on the copy engines (no SM involvement): the "push" form of
+// the gradient exchange sends this rank's region into every peer's inbox while the SMs run the projection VJP
+extern "C" int rs_peer_copy(void* dst, const void* src, long long bytes, void* stream) {
+  if (bytes < 0 || (bytes > 0 && (!dst || !src))) return RS_ERR_BAD_ARG;
+  if (bytes == 0) return RS_OK;
+  cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}
+
 // flag_arrays (DEVICE array of n_ranks pointers): rank g's flag array (u64[n_ranks]) as mapped in this process;
 // writes `value` into slot my_rank of every rank's array, after all earlier work of `stream`.
 extern "C" int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsigned long long value,

@@ -95,10 +95,13 @@ class ShGradExchange:
     (``rs_sh_coeffs_gather``), in a fixed (rank, camera) order, so all replicas hold bit-identical gradients.  At sh3
     this replaces a 192 B/Gaussian all-reduce (ring traffic 2(G-1)/G x 192 B) by (G-1) x 16 B/Gaussian of reads.
 
-    ``mode="p2p"``: the regions live in CUDA-IPC-shared device memory and the gather kernel reads the other ranks'
-    rows directly over NVLink; a flag handshake (remote store / local spin, ``rs_peer_signal`` / ``rs_peer_wait``)
-    orders publication before consumption, and two regions alternate so a rank may start its next backward while a
-    slower peer still reads the previous one.  ``mode="allgather"``: the regions are ordinary tensors, all-gathered
+    ``mode="push"`` (default): every rank owns an inbox per rank in CUDA-IPC-shared device memory; right after the
+    colour backward a rank copies its region into its slot of every peer's inbox with the COPY ENGINES (no SMs), on
+    side streams, while the SMs run the projection VJP, then raises its flag at the peers; the gather kernel waits
+    for the flags and reads only local memory.  ``mode="p2p"``: no copies, the gather kernel reads the other ranks'
+    rows directly over NVLink (pull).  In both, a flag handshake (remote store / local spin, ``rs_peer_signal`` /
+    ``rs_peer_wait``) orders publication before consumption, and two regions alternate so a rank may start its next
+    backward while a slower peer still reads the previous one.  ``mode="allgather"``: the regions are ordinary tensors, all-gathered
     with ``torch.distributed`` (NCCL, or gloo-free single process), then the same kernel reads the local copy.
 
     Usage per step::
@@ -109,7 +112,7 @@ class ShGradExchange:
         params["sh_coeffs"].grad = ex.finish()
     """
 
-    def __init__(self, n_gaussians: int, cams_per_rank: int, device, group=None, mode: str = "p2p",
+    def __init__(self, n_gaussians: int, cams_per_rank: int, device, group=None, mode: str = "push",
                  timeout_ms: int = 5000):
         from radegs_b200 import backend as be
         import ctypes
@@ -139,7 +142,7 @@ class ShGradExchange:
             cams = [int(c) for c in got]
         self.cams = cams
         with torch.cuda.device(self.device):
-            if mode == "p2p":
+            if mode in ("p2p", "push"):
                 self._init_p2p()
             elif mode == "allgather":
                 if len(set(cams)) != 1:
@@ -159,7 +162,9 @@ class ShGradExchange:
 
     def _init_p2p(self):
         ct, lib, be = self.ct, self.lib, self.be
-        regions = self._alloc(2 * self.region_stride)         # two alternating regions
+        # slot (g, parity) at offset (2 g + parity) * stride: rank g's region of the steps with that parity.  In pull
+        # mode only a rank's own slots are ever written; in push mode the peers fill the others by DMA.
+        regions = self._alloc(2 * self.world * self.region_stride)
         flags = self._alloc(256)                               # u64[world], written by the peers
         hb = lib.rs_peer_handle_bytes()
         handles = []
@@ -186,6 +191,7 @@ class ShGradExchange:
             self.region_base.append(mapped[0])
             self.flag_base.append(mapped[1])
         self.flag_ptrs_dev = torch.tensor(self.flag_base, dtype=torch.int64, device=self.device)
+        self._copy_streams = [torch.cuda.Stream(self.device) for _ in range(min(4, max(self.world - 1, 1)))]
         if self.world > 1:
             dist.barrier(group=self.group)                     # every mapping exists before anyone signals
 
@@ -222,18 +228,43 @@ class ShGradExchange:
             raise RuntimeError(f"ShGradExchange was built for {self.C} cameras x {self.N} Gaussians, got {C} x {N}")
         if self._pending is not None:
             raise RuntimeError("one fused SH-colour backward per step (call begin_step() before the next one)")
-        if self.mode == "p2p":
-            return self.ct.c_void_p(self.region_base[self.rank] + self._parity() * self.region_stride)
+        if self.mode in ("p2p", "push"):
+            return self.ct.c_void_p(self.region_base[self.rank] + self._slot(self.rank))
         return self.be.ptr(self.local[self._parity()])
+
+    def _slot(self, g: int) -> int:
+        return (2 * g + self._parity()) * self.region_stride
 
     def published(self, means: Tensor, degree: int, K: int, stream_ptr):
         """Called right after rs_sh_colors_bwd_local was queued: tell the peers (p2p) and remember the inputs.
         (Queuing the wait + gather kernels here on a side stream, to overlap the projection VJP, was measured SLOWER
         at N=2 -- 2.66 vs 2.58 ms/step: that kernel fills the register file, so the two only take turns.)"""
         self._pending = (means, int(degree), int(K))
+        be, lib, ct = self.be, self.lib, self.ct
         if self.mode == "p2p":
-            self.be.check(self.lib.rs_peer_signal(self.be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step,
-                                                  stream_ptr), "rs_peer_signal")
+            be.check(lib.rs_peer_signal(be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step, stream_ptr),
+                     "rs_peer_signal")
+        elif self.mode == "push":
+            main = torch.cuda.current_stream(self.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            src = self.region_base[self.rank] + self._slot(self.rank)
+            peers = [g for g in range(self.world) if g != self.rank]
+            streams = self._copy_streams
+            for s_ in streams:
+                s_.wait_event(fork)
+            for i, g in enumerate(peers):          # start with the next rank so the ranks do not all hit rank 0 first
+                g = peers[(i + self.rank) % len(peers)]
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    be.check(lib.rs_peer_copy(ct.c_void_p(self.region_base[g] + self._slot(self.rank)), ct.c_void_p(src),
+                                              self.region_bytes, be.stream_ptr(self.device)), "rs_peer_copy")
+            for s_ in streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(s_)
+                streams[0].wait_event(ev)
+            with torch.cuda.stream(streams[0]):    # the flag goes up only after every copy has landed
+                be.check(lib.rs_peer_signal(be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step,
+                                            be.stream_ptr(self.device)), "rs_peer_signal")
 
     def _out_buffer(self, K: int) -> Tensor:
         """Two persistent result buffers alternate (the previous step's gradient stays valid for one more step)."""
@@ -252,10 +283,13 @@ class ShGradExchange:
         out = self._out_buffer(K)
         with torch.cuda.device(self.device):
             st = be.stream_ptr(self.device)
-            if self.mode == "p2p":
+            if self.mode in ("p2p", "push"):
                 be.check(lib.rs_peer_wait(ct.c_void_p(self.flag_base[self.rank]), self.world, self.step,
                                           self.timeout_ms, be.ptr(self.timed_out), st), "rs_peer_wait")
-                bases = [b + self._parity() * self.region_stride for b in self.region_base]
+                if self.mode == "p2p":      # pull: rank g's slot in rank g's memory
+                    bases = [self.region_base[g] + self._slot(g) for g in range(self.world)]
+                else:                       # push: rank g's slot in MY inbox
+                    bases = [self.region_base[self.rank] + self._slot(g) for g in range(self.world)]
             else:
                 if self.world > 1:
                     dist.all_gather_into_tensor(self.gathered.view(-1), self.local[self._parity()], group=self.group)

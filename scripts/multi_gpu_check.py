@@ -57,7 +57,7 @@ if rank == 0:
         for r, g in zip(ref, step([c], None, False)):
             r += g
 report = {}
-for mode in ("p2p", "allgather"):
+for mode in ("push", "p2p", "allgather"):
     try:
         ex = ShGradExchange(N, 1, dev, mode=mode)
     except Exception as e:  # noqa: BLE001

@@ -629,7 +629,7 @@ def test_sh_gradient_split_over_virtual_ranks(cuda_dev, degree, cams):
     assert bool((v_coeffs[:, nb:] == 0).all()), "bands above the active degree get exact zeros"
 
 
-@pytest.mark.parametrize("mode", ["p2p", "allgather"])
+@pytest.mark.parametrize("mode", ["push", "p2p", "allgather"])
 def test_sh_grad_exchange_single_process(cuda_dev, mode):
     """ShGradExchange with one rank (signal to self / local gather) through the full rasterization() backward:
     same gradients as the plain path, on two consecutive steps (alternating regions)."""
