@@ -367,6 +367,7 @@ def fp32_accounting(wl, lib, backend, st, device):
             "warp_evaluations_blending": blends, "fwd_algorithmic_tflops": round(f, 2),
             "bwd_algorithmic_tflops": round(b, 2), "fma_probe_tflops": round(peak, 2),
             "fwd_frac_of_probe": round(f / peak, 3), "bwd_frac_of_probe": round(b / peak, 3),
+            "warp_block": "8x8 pixels (two per lane)" if lib.rs_raster_get_variant() == 1 else "8x4 pixels",
             "note": "algorithmic flops count every pair the reference's per-pixel loop visits (SURVEY 8d); the "
                     "kernels skip most of them with the warp-level footprint test, so this is work-equivalent "
                     "throughput, not executed flops"}
@@ -583,7 +584,7 @@ def main():
         key = "rs_rasterize_bwd"
         alg_bytes = M * (52 + 4 * D) + P * (4 * D + 36)           # SURVEY 8d, without the atomic-commit term
         achieved = alg_bytes / (st[key] * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd_kernel<4,256,false>", "achieved": achieved,
+        line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd2_kernel<128,false> (8x8 pixels per warp, two per lane)", "achieved": achieved,
                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "peak_source": how, "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
                             "note": "compositing is FP32-issue-bound, not HBM-bound (SURVEY 8d; ncu: issue-active "

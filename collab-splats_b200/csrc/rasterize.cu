@@ -426,7 +426,7 @@ __device__ __forceinline__ float sigma_col(float adx2, float bdx, float c, float
 // count of the (issue-bound) alpha test; 4 warps (128 threads) per tile, 128-Gaussian batches.
 constexpr int RT2 = 128;
 
-template <int DP, int BATCH>
+template <int DP, int BATCH, bool STATS>
 __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
 #pragma unroll
     for (int k = 0; k < DP; ++k) acc[h][k] = 0.f;
   int last_id[2] = {start - 1, start - 1}, med_id[2] = {-1, -1};
+  int st_contrib[2] = {0, 0}, st_term[2] = {-1, -1}, st_evals = 0, st_blend = 0;  // STATS only
 
   const int nb = (end - start + BATCH - 1) / BATCH;
   if (nb > 0) {
@@ -504,6 +505,11 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
             alpha[h] = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
             ok[h] = sig >= 0.f && alpha[h] >= RS_ALPHA_MIN;
           }
+          if constexpr (STATS) {
+            ++st_evals;
+            st_blend += __any_sync(RS_FULL_MASK, (ok[0] && T[0] * (1.f - alpha[0]) > RS_T_STOP) ||
+                                                     (ok[1] && T[1] * (1.f - alpha[1]) > RS_T_STOP));
+          }
           if (ok[0] || ok[1]) {
             const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
             const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
@@ -513,8 +519,9 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
               if (ok[h]) {
                 const float nT = T[h] * (1.f - alpha[h]);
                 if (!(nT > RS_T_STOP)) {
-                  if (T[h] != 0.f) { T_out[h] = T[h]; T[h] = 0.f; }
+                  if (T[h] != 0.f) { T_out[h] = T[h]; T[h] = 0.f; if constexpr (STATS) st_term[h] = base_idx + jj; }
                 } else {
+                  if constexpr (STATS) ++st_contrib[h];
                   const float vis = alpha[h] * T[h];
                   const float tt = tb + q2.z * dy[h];
                   dsum[h] += vis * tt;
@@ -546,6 +553,25 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
     }
   }
   rs::cp_async_wait_all();
+
+  if constexpr (STATS) {   // same counters as the one-pixel kernel; evaluations are per (8x8 warp block, Gaussian)
+    unsigned long long q = 0, qc = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (inside[h]) {
+        q += (unsigned long long)((st_term[h] >= 0 ? st_term[h] + 1 : end) - start);
+        qc += (unsigned long long)st_contrib[h];
+      }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      q += __shfl_xor_sync(RS_FULL_MASK, q, d);
+      qc += __shfl_xor_sync(RS_FULL_MASK, qc, d);
+    }
+    if (lane == 0) {
+      atomicAdd(a.stats + 0, q); atomicAdd(a.stats + 1, qc);
+      atomicAdd(a.stats + 2, (unsigned long long)st_evals); atomicAdd(a.stats + 3, (unsigned long long)st_blend);
+    }
+  }
 
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -998,13 +1024,14 @@ static int g_raster_variant = 1;  // DP == 4 only.  0: one pixel per lane (8x4 p
 
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
-    if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
     if (g_raster_variant == 1) {
       constexpr int B2 = 128;
       const size_t smem = sizeof(Smem<DP, B2>);
-      rasterize_fwd2_kernel<DP, B2><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);
+      if (a.stats) rasterize_fwd2_kernel<DP, B2, true><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);  // counting only
+      else rasterize_fwd2_kernel<DP, B2, false><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
+    if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
   }
   return launch_fwd2<DP, false>(a, st);
 }

@@ -7,7 +7,7 @@ $CMD > gpurun_out/profile_plain.log 2>&1 || { echo "plain run failed"; tail -20 
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on --profile-from-start off -k 'regex:rasterize_|radix_scatter|project_bwd|sh_colors' \
+ncu --set full --clock-control none --import-source on --profile-from-start off -k 'regex:rasterize_|radix_scatter|radix_hist|project_|sh_colors|isect_|scan_kernel|pack_geom|unpack_geom|rade_loss|offset_encode' \
     -o gpurun_out/prof_raster -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out

@@ -1,0 +1,22 @@
+"""Condenses an .ncu-rep (ncu --set full) into the per-kernel CSV kept under profiles/.
+    python scripts/ncu_summary.py gpurun_out/prof_raster.ncu-rep > profiles/rNN_ncu_full_summary.csv"""
+import csv, io, subprocess, sys
+cols = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct",
+        "smsp__inst_executed_op_global_red.sum", "smsp__sass_inst_executed_op_shared_ld.sum"]
+raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units = rows[0], rows[1]
+idx = [hdr.index(c) if c in hdr else None for c in cols]
+w = csv.writer(sys.stdout)
+print("# ncu --set full --clock-control none --import-source on, one resident bench step (bench.py --profile-step)")
+w.writerow(cols)
+w.writerow([units[i] if i is not None else "" for i in idx])
+for r in rows[2:]:
+    if len(r) < len(hdr): continue
+    w.writerow([r[i] if i is not None else "" for i in idx])
