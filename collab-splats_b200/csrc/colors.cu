@@ -30,34 +30,58 @@ __device__ __forceinline__ void camera_position(const float* __restrict__ vm, fl
   pz = -(i20 * tx + i21 * ty + i22 * tz);
 }
 
-// cooperative, coalesced copy of `count` coefficient rows (row = K*3 floats) global <-> shared (stride RS)
-__device__ __forceinline__ void rows_to_smem(float* s, const float* __restrict__ src, int count, int row, int RS,
-                                             int t) {
+// cooperative, coalesced copy of `count` coefficient rows (row = K*3 floats) global <-> shared (stride RS).
+// The flat index -> (row, column) split is a division by `row`: ROW > 0 makes it a compile-time constant
+// (K = 16 -> 48 floats, the sh3 case that carries the bandwidth), ROW == 0 keeps the generic run-time form.
+template <int ROW>
+__device__ __forceinline__ void rows_to_smem_t(float* s, const float* __restrict__ src, int count, int row_rt, int RS,
+                                               int t) {
+  const int row = ROW > 0 ? ROW : row_rt;
   const int total = count * row;
   if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     for (int i = t; i < total / 4; i += CB) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
       const float vv[4] = {v.x, v.y, v.z, v.w};
+      const int f0 = i * 4, r0 = f0 / row, c0 = f0 - r0 * row;   // one division per 16 bytes; row % 4 == 0 or wrap below
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int f = i * 4 + k; s[(f / row) * RS + (f % row)] = vv[k]; }
+      for (int k = 0; k < 4; ++k) {
+        int r = r0, c = c0 + k;
+        if (c >= row) { c -= row; ++r; }
+        s[r * RS + c] = vv[k];
+      }
     }
   } else {
     for (int f = t; f < total; f += CB) s[(f / row) * RS + (f % row)] = __ldg(src + f);
   }
 }
-__device__ __forceinline__ void smem_to_rows(const float* s, float* __restrict__ dst, int count, int row, int RS,
-                                             int t) {
+template <int ROW>
+__device__ __forceinline__ void smem_to_rows_t(const float* s, float* __restrict__ dst, int count, int row_rt, int RS,
+                                               int t) {
+  const int row = ROW > 0 ? ROW : row_rt;
   const int total = count * row;
   if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     for (int i = t; i < total / 4; i += CB) {
       float vv[4];
+      const int f0 = i * 4, r0 = f0 / row, c0 = f0 - r0 * row;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int f = i * 4 + k; vv[k] = s[(f / row) * RS + (f % row)]; }
+      for (int k = 0; k < 4; ++k) {
+        int r = r0, c = c0 + k;
+        if (c >= row) { c -= row; ++r; }
+        vv[k] = s[r * RS + c];
+      }
       reinterpret_cast<float4*>(dst)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
   } else {
     for (int f = t; f < total; f += CB) dst[f] = s[(f / row) * RS + (f % row)];
   }
+}
+__device__ __forceinline__ void rows_to_smem(float* s, const float* __restrict__ src, int count, int row, int RS, int t) {
+  if (row == 48) rows_to_smem_t<48>(s, src, count, row, RS, t);
+  else rows_to_smem_t<0>(s, src, count, row, RS, t);
+}
+__device__ __forceinline__ void smem_to_rows(const float* s, float* __restrict__ dst, int count, int row, int RS, int t) {
+  if (row == 48) smem_to_rows_t<48>(s, dst, count, row, RS, t);
+  else smem_to_rows_t<0>(s, dst, count, row, RS, t);
 }
 
 __global__ void __launch_bounds__(CB)

@@ -169,29 +169,61 @@ isect_emit_kernel(const float2* __restrict__ means2d, const int2* __restrict__ r
 // the depth bits) and writes its tile keys at cum[p] - count, so the emitted stream is already sorted by
 // (depth, flatten id, tile y, tile x) -- exactly what the first four 8-bit passes of the LSD sort over the 64-bit
 // keys produce from the (flatten id, y, x) emission order.  Only the (camera | tile) bits remain to be sorted.
+// Warp-cooperative: lane l describes entry p = warp_first + l (tile box, key bits, output offset); the warp's
+// intersections form ONE contiguous output range, and the lanes then write it item by item (lane k handles items
+// k, k + 32, ...), so the 8-byte key and 4-byte id stores are fully coalesced however uneven the tile counts are.
 __global__ void __launch_bounds__(IB)
 isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii,
                           const float* __restrict__ depths, const int32_t* __restrict__ order,
                           const long long* __restrict__ cum, int C, int N, int tile_w, int tile_h, int tile_bits,
                           long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+  constexpr int WARPS = IB / 32;
+  __shared__ int s_pref[WARPS][33];
+  __shared__ int s_xmin[WARPS][32], s_ymin[WARPS][32], s_w[WARPS][32], s_e[WARPS][32];
+  __shared__ unsigned long long s_key[WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long p = (long long)blockIdx.x * IB + threadIdx.x;
-  if (p >= (long long)C * N) return;
-  const int e = __ldg(order + p);
-  int xmin, ymin, xmax, ymax;
-  if (!tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax)) return;
-  const int cnt = (xmax - xmin) * (ymax - ymin);
-  if (cnt <= 0) return;
-  long long pos = __ldg(cum + p) - cnt;
-  const long long cam = e / N;
-  const unsigned long long hi_cam = (unsigned long long)cam << (32 + tile_bits);
-  const unsigned long long dbits = (unsigned long long)__float_as_uint(__ldg(depths + e));
-  for (int y = ymin; y < ymax; ++y)
-    for (int x = xmin; x < xmax; ++x) {
-      unsigned long long tile = (unsigned long long)(y * tile_w + x);
-      isect_ids[pos] = (long long)(hi_cam | (tile << 32) | dbits);
-      flatten_ids[pos] = (int32_t)e;
-      ++pos;
+  const long long total = (long long)C * N;
+  int cnt = 0, xmin = 0, ymin = 0, xmax = 0, ymax = 0, e = 0;
+  long long cum_p = 0;
+  if (p < total) {
+    e = __ldg(order + p);
+    cum_p = __ldg(cum + p);
+    if (tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax))
+      cnt = max((xmax - xmin) * (ymax - ymin), 0);
+  }
+  int incl = cnt;   // inclusive prefix of the counts inside the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(RS_FULL_MASK, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const int warp_total = __shfl_sync(RS_FULL_MASK, incl, 31);
+  if (warp_total == 0) return;
+  // output offset of the warp's first item: every lane knows cum_p - incl (they are all equal where p < total)
+  const long long base = __shfl_sync(RS_FULL_MASK, cum_p - incl, 0);
+  s_pref[warp][lane + 1] = incl;
+  if (lane == 0) s_pref[warp][0] = 0;
+  s_xmin[warp][lane] = xmin; s_ymin[warp][lane] = ymin; s_w[warp][lane] = xmax - xmin; s_e[warp][lane] = e;
+  if (cnt > 0) {
+    const unsigned long long cam = (unsigned long long)(e / N);
+    s_key[warp][lane] = (cam << (32 + tile_bits)) | (unsigned long long)__float_as_uint(__ldg(depths + e));
+  }
+  __syncwarp();
+  for (int k = lane; k < warp_total; k += 32) {
+    int lo = 0, hi = 32;   // owner j: pref[j] <= k < pref[j+1]
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (s_pref[warp][mid] <= k) lo = mid; else hi = mid;
     }
+    const int r = k - s_pref[warp][lo];
+    const int w = s_w[warp][lo];
+    const int ry = r / w, rx = r - ry * w;
+    const unsigned long long tile = (unsigned long long)((s_ymin[warp][lo] + ry) * tile_w + s_xmin[warp][lo] + rx);
+    isect_ids[base + k] = (long long)(s_key[warp][lo] | (tile << 32));
+    flatten_ids[base + k] = s_e[warp][lo];
+  }
 }
 
 __global__ void __launch_bounds__(IB)

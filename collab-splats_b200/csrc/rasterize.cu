@@ -793,8 +793,8 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
 // x-dependent terms and -- the point of the variant -- ONE 16-value warp reduction and ONE 64-byte RED per
 // (warp, Gaussian): their contributions are summed in registers first.  Because dx is common to the two pixels
 // the record's moments factor as dx * (sum over the two pixels), which removes most per-pixel multiplies.
-template <int BATCH, bool ABSGRAD>
-__global__ void __launch_bounds__(RT2, 4) rasterize_bwd2_kernel(const RasterArgs a) {
+template <int BATCH, bool ABSGRAD, int MINB>
+__global__ void __launch_bounds__(RT2, MINB) rasterize_bwd2_kernel(const RasterArgs a) {
   constexpr int DP = 4;
   static_assert(BATCH == RT2, "one id per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1020,6 +1020,7 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   rasterize_fwd_kernel<DP, B, STATS><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
+static int g_bwd2_minb = 4;   // tuning knob (rs_raster_set_occupancy): register cap of the 2-px backward
 static int g_raster_variant = 1;  // DP == 4 only.  0: one pixel per lane (8x4 per warp); 1 (default): two pixels per lane (8x8 per warp)
 
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
@@ -1053,8 +1054,11 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
       constexpr int B2 = RT2;
       const size_t smem = sizeof(Smem<DP, B2>);
       const int grid = a.C * a.tile_w * a.tile_h;
-      if (a.abs_grad) rasterize_bwd2_kernel<B2, true><<<grid, RT2, smem, st>>>(a);
-      else rasterize_bwd2_kernel<B2, false><<<grid, RT2, smem, st>>>(a);
+      // MINB = CTAs per SM the register allocation is capped for: 4 -> 94 registers, 6 -> 80, 7 -> 72 (no spills)
+      if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4><<<grid, RT2, smem, st>>>(a);
+      else if (g_bwd2_minb == 7) rasterize_bwd2_kernel<B2, false, 7><<<grid, RT2, smem, st>>>(a);
+      else if (g_bwd2_minb == 6) rasterize_bwd2_kernel<B2, false, 6><<<grid, RT2, smem, st>>>(a);
+      else rasterize_bwd2_kernel<B2, false, 4><<<grid, RT2, smem, st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
   }
@@ -1082,6 +1086,7 @@ extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 // tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
 extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
 extern "C" int rs_raster_get_variant(void) { return g_raster_variant; }
+extern "C" void rs_raster_set_occupancy(int min_blocks) { g_bwd2_minb = (min_blocks == 6 || min_blocks == 7) ? min_blocks : 4; }
 // footprint test used by rs_pack_geom AND the compositing kernels (set it before rs_pack_geom and leave it until
 // the backward has run): 0 = padded bbox of the alpha >= 1/255 ellipse, 1 (default) = exact ellipse-vs-rectangle
 extern "C" void rs_raster_set_cull_mode(int m) { g_cull_mode = m ? 1 : 0; }

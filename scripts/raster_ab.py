@@ -26,8 +26,8 @@ def step():
     return [t.detach() for t in o[:5]], [t.grad.clone() for t in p]
 ref = None
 default = lib.rs_raster_get_variant()
-for variant, cull in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 0), (1, 1)):
-    lib.rs_raster_set_variant(variant); lib.rs_raster_set_cull_mode(cull)
+for variant, cull, occ in ((0, 1, 4), (1, 1, 4), (1, 1, 6), (1, 1, 7), (1, 1, 4), (1, 1, 6), (1, 1, 7)):
+    lib.rs_raster_set_variant(variant); lib.rs_raster_set_cull_mode(cull); lib.rs_raster_set_occupancy(occ)
     for _ in range(3): o, g = step()
     lib.rs_timing_enable(1)
     for _ in range(10): o, g = step()
@@ -36,6 +36,6 @@ for variant, cull in ((0, 0), (1, 0), (0, 1), (1, 1), (1, 0), (1, 1)):
     if ref is None: ref = (o, g)
     err = max(float((a - b).abs().max()) for a, b in zip(o, ref[0]))
     gerr = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g, ref[1]))
-    print(f"variant {variant} cull {cull}: fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
+    print(f"variant {variant} cull {cull} occ {occ}: sh_fwd {s['rs_sh_colors_fwd'][0] / 10:.4f} sh_bwd {s['rs_sh_colors_bwd'][0] / 10:.4f} emit {s['rs_isect_emit_ordered'][0] / 10:.4f} fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
           f"unpack {s['rs_unpack_geom_grad'][0] / 10:.4f} ms   max|out diff vs first| {err:.2e}  max rel grad diff {gerr:.2e}")
-lib.rs_raster_set_variant(default); lib.rs_raster_set_cull_mode(1)
+lib.rs_raster_set_variant(default); lib.rs_raster_set_cull_mode(1); lib.rs_raster_set_occupancy(4)
