@@ -657,6 +657,16 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
 #pragma unroll
     for (int k = 0; k < DP; ++k) v_c[k] *= (k == a.ed_channel) ? sc : 1.f;
   }
+  // Wide colour rows (>= 32 channels): the per-Gaussian colour gradient sum_p vis[p] * v_c[p][k] is formed with
+  // LANES = CHANNELS (each lane owns channels lane, lane + 32, ...), walking the warp's contributing pixels: vis[p]
+  // is broadcast by one shuffle, v_c[p][.] is read from shared memory (conflict free) and the totals land one channel
+  // per lane, i.e. as coalesced REDs -- instead of 31 shuffle exchanges per 32 channels with lanes = pixels.
+  constexpr bool CHLANE = DP >= 32;
+  float* s_vc = reinterpret_cast<float*>(smem_raw + sizeof(Smem<DP, BATCH>));   // [RT][DP], CHLANE only
+  if constexpr (CHLANE) {
+#pragma unroll
+    for (int k = 0; k < DP; ++k) s_vc[t * DP + k] = v_c[k];   // (after the ED rescale above; made visible by the barrier below)
+  }
   const int last_id = inside ? a.last_ids[pix] : start - 1;
   const float il = inside ? inv_ray_len(a, c.cam, px, py) : 0.f;
 #if RS_NORMALIZE_EXPECTED_DEPTH
@@ -778,7 +788,43 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         }
         if constexpr (DP > 4) {
           const int row = a.color_per_cam ? id : id % a.N;
-          commit_color_grads<DP, 0>(v_c, vis, a.color_grad + (size_t)row * DP, a.D, lane);
+          if constexpr (CHLANE) {
+            constexpr int NCH = (DP + 31) / 32;
+            float acc[NCH];
+#pragma unroll
+            for (int cch = 0; cch < NCH; ++cch) acc[cch] = 0.f;
+            unsigned nz = __ballot_sync(RS_FULL_MASK, vis != 0.f);
+            const float* rows = s_vc + (size_t)(warp * 32) * DP + lane;
+            constexpr int UN = 4;   // contributing pixels per round (8 measured slower, 1 latency-bound): their shuffles and row loads are independent
+            while (nz) {
+              int pl[UN];
+              float vp[UN];
+#pragma unroll
+              for (int u = 0; u < UN; ++u) {
+                pl[u] = nz ? __ffs(nz) - 1 : 0;
+                const bool on = nz != 0;
+                nz &= nz - 1;
+                vp[u] = __shfl_sync(RS_FULL_MASK, vis, pl[u]);
+                vp[u] = on ? vp[u] : 0.f;
+              }
+              float rv[UN][NCH];
+#pragma unroll
+              for (int u = 0; u < UN; ++u)
+#pragma unroll
+                for (int cch = 0; cch < NCH; ++cch)
+                  rv[u][cch] = (cch * 32 + 32 <= DP || cch * 32 + lane < DP) ? rows[pl[u] * DP + cch * 32] : 0.f;
+#pragma unroll
+              for (int u = 0; u < UN; ++u)
+#pragma unroll
+                for (int cch = 0; cch < NCH; ++cch) acc[cch] = fmaf(vp[u], rv[u][cch], acc[cch]);
+            }
+            float* dst = a.color_grad + (size_t)row * DP + lane;
+#pragma unroll
+            for (int cch = 0; cch < NCH; ++cch)
+              if (cch * 32 + lane < a.D) atomicAdd(dst + cch * 32, acc[cch]);
+          } else {
+            commit_color_grads<DP, 0>(v_c, vis, a.color_grad + (size_t)row * DP, a.D, lane);
+          }
         }
       }
     }
@@ -1039,9 +1085,13 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
 
 static unsigned long long* g_raster_stats = nullptr;
 static int g_cull_mode = 1;  // 0: bbox of the footprint ellipse; 1 (default): exact ellipse-vs-rectangle test
+// backward batch: wide rows also keep the tile's v_c rows (RT x DP floats) in shared memory, so the staged batches
+// are halved there to keep two CTAs per SM
+template <int DP> struct BwdBatch { static constexpr int value = DP >= 64 ? 32 : Batch<DP>::value; };
+
 template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
-  constexpr int B = Batch<DP>::value;
-  const size_t smem = sizeof(Smem<DP, B>);
+  constexpr int B = BwdBatch<DP>::value;
+  const size_t smem = sizeof(Smem<DP, B>) + (DP >= 32 ? sizeof(float) * RT * DP : 0);
   cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B, ABSGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
