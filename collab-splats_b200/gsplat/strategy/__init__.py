@@ -178,11 +178,9 @@ class DefaultStrategy(Strategy):
         if packed:
             raise NotImplementedError("packed=True is not on the collab-splats path")
         m2 = info[self.key_for_gradient]
-        grads = (m2.absgrad if self.absgrad else m2.grad).clone()
-        grads[..., 0] *= info["width"] / 2.0 * info["n_cameras"]
-        grads[..., 1] *= info["height"] / 2.0 * info["n_cameras"]
+        raw = m2.absgrad if self.absgrad else m2.grad
         n = len(list(params.values())[0])
-        dev = grads.device
+        dev = raw.device
         if state["grad2d"] is None:
             state["grad2d"] = torch.zeros(n, device=dev)
         if state["count"] is None:
@@ -190,6 +188,27 @@ class DefaultStrategy(Strategy):
         if self.refine_scale2d_stop_iter > 0 and state["radii"] is None:
             state["radii"] = torch.zeros(n, device=dev)
         radii = info["radii"]
+        sx = info["width"] / 2.0 * info["n_cameras"]
+        sy = info["height"] / 2.0 * info["n_cameras"]
+        if raw.is_cuda and radii.dim() == 3:
+            # one fused pass over [C,N] (csrc/stats.cu: rs_densify_stats) instead of the clone / scale / mask / gather /
+            # norm / index_add chain below
+            from radegs_b200 import backend as _be
+            lib = _be.load()
+            C_, N_ = radii.shape[:2]
+            g = raw.to(torch.float32).contiguous()
+            r32 = radii.to(torch.int32).contiguous()
+            with torch.cuda.device(dev):
+                _be.check(lib.rs_densify_stats(
+                    _be.ptr(g), _be.ptr(r32), C_, N_, sx, sy, 1.0 / float(max(info["width"], info["height"])),
+                    _be.ptr(state["grad2d"]), _be.ptr(state["count"]),
+                    _be.ptr(state["radii"]) if self.refine_scale2d_stop_iter > 0 else None, _be.stream_ptr(dev)),
+                    "rs_densify_stats")
+            return
+        # host tensors (CPU tests of the bookkeeping): the published gsplat sequence
+        grads = raw.clone()
+        grads[..., 0] *= sx
+        grads[..., 1] *= sy
         sel = (radii > 0).all(dim=-1) if radii.dim() == 3 else radii > 0      # [C,N]
         gs_ids = torch.where(sel)[1]
         state["grad2d"].index_add_(0, gs_ids, grads[sel].norm(dim=-1))

@@ -217,6 +217,17 @@ int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsig
 int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long long value, int timeout_ms, int* timed_out_dev,
                  void* stream);
 
+/* ---- per-Gaussian bookkeeping after the backward.
+ * rs_densify_stats: what gsplat's DefaultStrategy._update_state accumulates (reached from
+ * collab_splats/models/rade_gs_model.py:191-198): grad2d[n] += sum over visible cameras of |(gx*sx, gy*sy)|,
+ * count[n] += number of visible cameras, radii_max[n] = max(radii_max[n], max(rx, ry) * inv_extent); visible =
+ * both radii > 0.  rs_project_lookup: collab_splats/utils/utils.py:13-40 (project_gaussians) on the device. */
+int rs_densify_stats(const float* grads /* [C,N,2] */, const int32_t* radii /* [C,N,2] */, int C, int N, float sx,
+                     float sy, float inv_extent, float* grad2d, float* count, float* radii_max /* NULL ok */,
+                     void* stream);
+int rs_project_lookup(const float* means2d /* [N,2] */, const int32_t* radii /* [N,2] */, int N, int width, int height,
+                      long long* proj_flattened /* [N] */, unsigned char* valid_mask /* [N] */, void* stream);
+
 /* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
  * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and
  * collab_splats/models/rade_gs_model.py:202-219,292-307 as run by the training step.
