@@ -80,6 +80,8 @@ _SIGNATURES = {
     "rs_peer_wait": (_i, [_p, _i, C.c_ulonglong, _i, _p, _p]),
     "rs_densify_stats": (_i, [_p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p]),
     "rs_project_lookup": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "rs_tsdf_integrate": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _p, _p, _f, _f, _f, _i, _i, _p, _p, _ll, _p, _i]
+                          + [_p] * 6 + [_p]),
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 

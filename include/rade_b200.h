@@ -228,6 +228,22 @@ int rs_densify_stats(const float* grads /* [C,N,2] */, const int32_t* radii /* [
 int rs_project_lookup(const float* means2d /* [N,2] */, const int32_t* radii /* [N,2] */, int N, int width, int height,
                       long long* proj_flattened /* [N] */, unsigned char* valid_mask /* [N] */, void* stream);
 
+/* ---- TSDF fusion of rendered frames on the device: replaces, in the meshing exporter
+ * collab_splats/utils/mesh.py:1562-1632, the per-frame `.cpu().numpy()` + Open3D ScalableTSDFVolume.integrate (CPU).
+ * Volume = hash map (64-bit packed unit coordinates, open addressing) from 16^3-voxel units to slots of a
+ * caller-owned pool.  Caller-owned state: keys u64[capacity] (all 0xFF), vals i32[capacity] (all -1), capacity a power
+ * of two > max_units; counters i32[4] = {units allocated, units touched by the last frame, overflow flag, -};
+ * unit_xyz i32[max_units,3]; stamps i32[capacity] (zero); touched i32[max_units]; tsdf, weight f32[max_units,4096];
+ * rgb f32[max_units,4096,3] or NULL -- all zero-initialised.  Voxel (x,y,z) of a unit is element x*256 + y*16 + z.
+ * frame ids start at 1 and must increase.  No host synchronisation, no allocation. */
+int rs_tsdf_integrate(const float* depth /* [H,W], 0 = none */, const unsigned char* color_u8 /* [H,W,3] or NULL */,
+                      const float* color_f32 /* [H,W,3] or NULL */, int width, int height, float fx, float fy,
+                      float cx, float cy, const float* extrinsic_3x4 /* host, world->camera */,
+                      const float* pose_3x4 /* host, camera->world */, float voxel_length, float sdf_trunc,
+                      float depth_trunc, int depth_sampling_stride, int frame_id, unsigned long long* keys,
+                      int* vals, long long capacity, int* counters, int max_units, int* unit_xyz, int* stamps,
+                      int* touched, float* tsdf, float* weight, float* rgb, void* stream);
+
 /* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
  * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and
  * collab_splats/models/rade_gs_model.py:202-219,292-307 as run by the training step.
