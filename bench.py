@@ -97,6 +97,27 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from the newest committed
+    ``ncu --set full`` summary under profiles/ (same command, see scripts/gpu_profile.sh); (None, why) if absent."""
+    import csv
+    files = sorted((ROOT / "profiles").glob("r*_ncu_full_summary.csv"))
+    if not files:
+        return None, "no profiles/r*_ncu_full_summary.csv"
+    rows = [r for r in csv.reader(l for l in files[-1].read_text().splitlines() if not l.startswith("#"))]
+    head, units = rows[0], rows[1]
+    try:
+        ir, iw = head.index("dram__bytes_read.sum"), head.index("dram__bytes_write.sum")
+    except ValueError:
+        return None, "summary has no dram byte columns"
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        if kernel_substr in r[0]:
+            return (float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0),
+                    f"profiles/{files[-1].name}")
+    return None, f"{kernel_substr} not in {files[-1].name}"
+
+
 # ------------------------------------------------------------------------------------------------ workload
 class Workload:
     """rade-gs training step on one view (collab_splats/models/rade_gs_model.py:80-309 restated on device)."""
@@ -584,8 +605,10 @@ def main():
         key = "rs_rasterize_bwd"
         alg_bytes = M * (52 + 4 * D) + P * (4 * D + 36)           # SURVEY 8d, without the atomic-commit term
         achieved = alg_bytes / (st[key] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic("rasterize_bwd")
         line["roofline"] = {"bound": "hbm", "kernel": "rasterize_bwd2_kernel<128,false> (8x8 pixels per warp, two per lane)", "achieved": achieved,
-                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                            "traffic_source": traffic_src,
                             "peak_source": how, "algorithmic_bytes": alg_bytes, "avg_launch_ms": st[key],
                             "note": "compositing is FP32-issue-bound, not HBM-bound (SURVEY 8d; ncu: issue-active "
                                     "~80%, DRAM ~2%); see DESIGN.md and profiles/"}

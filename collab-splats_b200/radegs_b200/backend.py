@@ -82,6 +82,9 @@ _SIGNATURES = {
     "rs_project_lookup": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "rs_tsdf_integrate": (_i, [_p, _p, _p, _i, _i, _f, _f, _f, _f, _p, _p, _f, _f, _f, _i, _i, _p, _p, _ll, _p, _i]
                           + [_p] * 6 + [_p]),
+    "rs_feature_hidden_fwd": (_i, [_p] + [_i] * 7 + [_p, _p, _i, _p, _p, _p]),
+    "rs_feature_branch": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _f] + [_p] * 6 + [_p]),
+    "rs_feature_hidden_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 

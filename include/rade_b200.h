@@ -244,6 +244,27 @@ int rs_tsdf_integrate(const float* depth /* [H,W], 0 = none */, const unsigned c
                       int* vals, long long capacity, int* counters, int max_units, int* unit_xyz, int* stamps,
                       int* touched, float* tsdf, float* weight, float* rgb, void* stream);
 
+/* ---- feature decode + cosine loss of the rade-features model: replaces
+ * collab_splats/models/rade_features_model.py:149-189 (decode_features: bilinear resize + TwoLayerMLP + per-branch
+ * resize), collab_splats/utils/features.py:408-449 (TwoLayerMLP) and rade_features_model.py:564-582 (weighted cosine
+ * loss), forward and backward.  render [H,W,ld] is the rasterizer's colour output, features are its columns
+ * ch0..ch0+F-1 (no permuted copy); x [Hm*Wm,F] and h [Hm*Wm,Hd] are caller-owned intermediates; F, Hd <= 128.
+ * Outputs of a branch are channel-first [C, Hb*Wb] like the reference's.  All v_* buffers and *loss are ACCUMULATED
+ * into (caller zero-fills).  rs_feature_branch with gt == NULL only decodes; with v_h == NULL it is forward-only. */
+int rs_feature_hidden_fwd(const float* render, int H, int W, int ld, int ch0, int F, int Hm, int Wm,
+                          const float* W1 /* [Hd,F] */, const float* b1 /* [Hd] */, int Hd, float* x, float* h,
+                          void* stream);
+int rs_feature_branch(const float* h, int Hm, int Wm, int Hd, const float* W2 /* [C,Hd] */, const float* b2 /* [C] */,
+                      int C, const float* gt /* [C,Hb*Wb] or NULL */, int Hb, int Wb,
+                      float scale /* branch weight * lambda / (Hb*Wb) */, float* loss /* [1] */,
+                      float* psum /* [Hb*Wb,3] zero-filled scratch, needed with gt */,
+                      float* v_h /* [Hm*Wm,Hd] or NULL */, float* v_W2 /* [C,Hd] */, float* v_b2 /* [C] */,
+                      float* decoded /* [C,Hb*Wb] or NULL */, void* stream);
+int rs_feature_hidden_bwd(const float* x, const float* h, const float* v_h, int Hm, int Wm, int Hd, int F,
+                          const float* W1, float* v_W1 /* [Hd,F] */, float* v_b1 /* [Hd] */,
+                          float* v_render /* [H,W,ld] or NULL */, int H, int W, int ld, int ch0,
+                          const float* gscale /* device scalar multiplying v_h, or NULL */, void* stream);
+
 /* ---- fused post-render loss: L1 on RGB + RaDe depth-normal consistency for one camera, forward
  * and gradients in one pass.  Replaces collab_splats/utils/camera_utils.py:176-279 (depth_double_to_normal) and
  * collab_splats/models/rade_gs_model.py:202-219,292-307 as run by the training step.
