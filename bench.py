@@ -394,6 +394,26 @@ def fp32_accounting(wl, lib, backend, st, device):
                     "throughput, not executed flops"}
 
 
+def stage_rooflines(st, CN, K, M, P, n_tiles, D, peak):
+    """Achieved algorithmic GB/s of the HBM-bound stages (bytes per unit: SURVEY 8d / DESIGN.md section 4) over
+    their in-step durations, as fractions of the measured HBM peak."""
+    passes_tile = 2                                   # camera|tile bits (13 + 1) in 8-bit digits
+    alg = {
+        "rs_project_fwd": 104 * CN, "rs_project_bwd": 136 * CN,
+        "rs_sh_colors_fwd": (12 * K + 40) * CN, "rs_sh_colors_bwd": 2 * (12 * K + 40) * CN,
+        "rs_isect_count": 20 * CN, "rs_argsort_u32": (4 + 16 * 4) * CN,      # 4 B hist read + 4 passes x (8 B in + 8 B out)
+        "rs_cumsum_gather_i32_i64": 16 * CN, "rs_isect_emit_ordered": 32 * CN + 12 * M,
+        "rs_sort_pairs": (8 + 24 * passes_tile) * M, "rs_offset_encode": 8 * M + 4 * n_tiles,
+        "rs_pack_geom": 124 * CN, "rs_unpack_geom_grad": 120 * CN, "rs_rade_loss_fwd_bwd": 90 * P,
+    }
+    out = {}
+    for k, b in alg.items():
+        if k in st and st[k] > 0:
+            gbs = b / (st[k] * 1e-3) / 1e9
+            out[k] = {"GBps": round(gbs, 1), "frac": round(gbs / peak, 3)}
+    return out
+
+
 def cpu_baseline_sample(cfg_id: int, threads: int):
     """CPU oracle (a restatement of the reference path, kind 'port') on a bounded sample of the workload: all
     Gaussians projected, a central 256x144 window of the view composited, fwd + loss + bwd."""
@@ -613,6 +633,8 @@ def main():
                             "note": "compositing is FP32-issue-bound, not HBM-bound (SURVEY 8d; ncu: issue-active "
                                     "~80%, DRAM ~2%); see DESIGN.md and profiles/"}
         line["fp32"] = fp32_accounting(wl, lib, backend, st, device)
+        line["stage_roofline_hbm"] = stage_rooflines(st, wl.cfg.n_gaussians, (wl.cfg.sh_degree + 1) ** 2, M, P,
+                                                     int(wl.last_meta["isect_offsets"].numel()), D, peak)
         line["stage_ms"] = {k: round(v, 4) for k, v in sorted(st.items(), key=lambda kv: -kv[1])}
         line["stage_ms"]["sum_of_library_kernels"] = round(sum(st.values()), 4)
         if world == 1 and not args.no_cpu_baseline:

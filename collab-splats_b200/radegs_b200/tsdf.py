@@ -157,7 +157,8 @@ class ScalableTSDFVolume:
 
 def fuse_render_sweep(volume: ScalableTSDFVolume, gaussians, viewmats: Tensor, Ks: Tensor, width: int, height: int,
                       sh_degree: Optional[int] = 3, depth_name: str = "depth", depth_trunc: float = 20.0,
-                      background: Optional[Tensor] = None, rasterize_mode: str = "antialiased") -> int:
+                      background: Optional[Tensor] = None, rasterize_mode: str = "antialiased",
+                      views_per_launch: int = 1) -> int:
     """The frame loop of ``Open3DTSDFFusion.main`` (collab_splats/utils/mesh.py:1571-1632) with every frame kept on
     the device: for each camera, render forward-only (``RadegsModel.get_outputs`` in eval mode: ``RGB+ED``,
     rade_gs_model.py:153-154,439-465), build the same ``rgb`` / ``depth`` outputs (rade_gs_model.py:227-262:
@@ -166,23 +167,30 @@ def fuse_render_sweep(volume: ScalableTSDFVolume, gaussians, viewmats: Tensor, K
     ``gaussians`` = (means, quats, scales, opacities, colors) already activated, as ``rasterization`` takes them;
     ``viewmats`` [V,4,4] world->camera (the extrinsic the reference hands to Open3D is exactly this matrix:
     ``inv(c2w @ diag(1,-1,-1,1))``, mesh.py:1592-1596,1630); ``depth_name`` "depth" (expected) or "median_depth".
-    Returns the number of frames integrated.  No per-frame host synchronisation."""
+    ``views_per_launch`` > 1 renders that many cameras per ``rasterization`` call (the camera axis of the
+    rasterizer; identical frames, fewer launches); frames are integrated in camera order either way.
+    Returns the number of frames integrated.  No per-frame host synchronisation besides the rasterizer's own
+    intersection-count read."""
     from gsplat.rendering import rasterization
     if depth_name not in ("depth", "median_depth"):
         raise ValueError("depth_name must be 'depth' or 'median_depth'")
+    if views_per_launch < 1:
+        raise ValueError("views_per_launch must be >= 1")
     means, quats, scales, opacities, colors = gaussians
     V = viewmats.shape[0]
     ext = viewmats.detach().double().cpu().numpy()
     Kh = Ks.detach().double().cpu().numpy()
     bg = background if background is not None else torch.zeros(3, device=means.device)
     with torch.no_grad():
-        for v in range(V):
+        for v0 in range(0, V, views_per_launch):
+            v1 = min(V, v0 + views_per_launch)
             render, alpha, exp_d, med_d, _, _ = rasterization(
-                means, quats, scales, opacities, colors, viewmats[v:v + 1], Ks[v:v + 1], width, height, packed=False,
+                means, quats, scales, opacities, colors, viewmats[v0:v1], Ks[v0:v1], width, height, packed=False,
                 sh_degree=sh_degree, render_mode="RGB+ED", rasterize_mode=rasterize_mode, return_depth_normal=True)
-            rgb = torch.clamp(render[0, ..., :3] + (1 - alpha[0]) * bg, 0.0, 1.0)
-            d = (exp_d if depth_name == "depth" else med_d)[0]
-            d = torch.where(alpha[0] > 0, d, d.max())
-            intr = PinholeCameraIntrinsic(width, height, Kh[v, 0, 0], Kh[v, 1, 1], Kh[v, 0, 2], Kh[v, 1, 2])
-            volume.integrate(d, (rgb * 255).to(torch.uint8), intr, ext[v], depth_trunc=depth_trunc)
+            rgb8 = (torch.clamp(render[..., :3] + (1 - alpha) * bg, 0.0, 1.0) * 255).to(torch.uint8)
+            d = exp_d if depth_name == "depth" else med_d
+            d = torch.where(alpha > 0, d, d.amax(dim=(1, 2, 3), keepdim=True))
+            for v in range(v0, v1):
+                intr = PinholeCameraIntrinsic(width, height, Kh[v, 0, 0], Kh[v, 1, 1], Kh[v, 0, 2], Kh[v, 1, 2])
+                volume.integrate(d[v - v0], rgb8[v - v0], intr, ext[v], depth_trunc=depth_trunc)
     return V

@@ -15,16 +15,16 @@ gs, vm, Ks = scenes.make_scene(cfg, n_views=n_views)
 p = [t.to(dev) for t in scenes.activate(gs, 3)]
 vmd, Kd = vm.to(dev), Ks.to(dev)
 out = {}
-for voxel, trunc in ((0.01, 0.03), (0.005, 0.015)):
+for voxel, trunc, vpl in ((0.01, 0.03, 1), (0.01, 0.03, 4), (0.005, 0.015, 1)):
     vol = tsdf.ScalableTSDFVolume(voxel, trunc, max_units=262144 if voxel < 0.01 else 65536, device=dev)
-    tsdf.fuse_render_sweep(vol, p, vmd[:2], Kd[:2], cfg.width, cfg.height, depth_trunc=20.0)   # warm-up
+    tsdf.fuse_render_sweep(vol, p, vmd[:4], Kd[:4], cfg.width, cfg.height, depth_trunc=20.0, views_per_launch=vpl)   # warm-up
     vol.reset()
     torch.cuda.synchronize()
     lib.rs_timing_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
-    tsdf.fuse_render_sweep(vol, p, vmd, Kd, cfg.width, cfg.height, depth_trunc=20.0)
+    tsdf.fuse_render_sweep(vol, p, vmd, Kd, cfg.width, cfg.height, depth_trunc=20.0, views_per_launch=vpl)
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -32,7 +32,7 @@ for voxel, trunc in ((0.01, 0.03), (0.005, 0.015)):
     lib.rs_timing_enable(0)
     U = vol.n_units()
     touched_last = int(vol.counters[1])
-    out[f"voxel_{voxel}"] = {
+    out[f"voxel_{voxel}_views_per_launch_{vpl}"] = {
         "views": n_views, "ms_per_view_device": round(e0.elapsed_time(e1) / n_views, 3),
         "ms_per_view_wall": round(wall * 1e3 / n_views, 3), "units_allocated": U,
         "units_touched_last_frame": touched_last,

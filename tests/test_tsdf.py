@@ -246,3 +246,7 @@ def test_fuse_render_sweep_equals_per_frame_host_loop(cuda_dev):
                           K[0, 0], K[1, 1], K[0, 2], K[1, 2], vm[v].double().numpy(), depth_trunc=6.0)
     assert len(ref.units) > 20
     _compare(vol, ref, True)
+    # several cameras per rasterization() call: same frames, same volume
+    vol3 = tsdf.ScalableTSDFVolume(0.02, 0.06, max_units=8192, device=cuda_dev)
+    tsdf.fuse_render_sweep(vol3, params, vmd, Kd, cfg.width, cfg.height, sh_degree=3, depth_trunc=6.0, views_per_launch=2)
+    _compare(vol3, ref, True)
