@@ -26,6 +26,11 @@ TILE_SIZE = 16
 #   "presort": argsort the C*N depths once, emit the keys in depth order, radix-sort only the (camera|tile) bits
 #   "radix":   emit in (camera, Gaussian, tile) order, radix-sort all 32 + tile_bits + cam_bits key bits
 ISECT_SORT_METHOD = "presort"
+# Which pipeline rasterization() uses for isect_tiles + isect_offset_encode (identical outputs; tests compare them):
+#   "radix": isect_tiles (ISECT_SORT_METHOD) + isect_offset_encode -- the fastest measured on B200, the default
+#   "chunk": per-camera depth argsort + chunked counting sort (csrc/chunksort.cu), no radix passes over the pairs
+#            (measured slower: scattered 12-byte stores, profiles/r01_chunk_ab.txt);  "tile": csrc/tilesort.cu
+ISECT_PIPELINE = "radix"
 # Set by radegs_b200.multiview.ShGradExchange while a camera-sharded multi-GPU step runs: the backward of the
 # fused SH colours then publishes per-camera colour gradients instead of producing the coefficient gradient.
 SH_GRAD_SINK = None
@@ -277,13 +282,65 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     return (tiles, ids_b, flat_b) if where == 0 else (tiles, ids_a, flat_a)
 
 
+def _isect_chunked(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int):
+    """csrc/chunksort.cu: tiles_per_gauss, sorted isect_ids / flatten_ids and isect_offsets without sorting the pairs."""
+    lib = _be.load()
+    C, N = depths.shape
+    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
+    _need_cuda(means2d, radii, depths)
+    dev = means2d.device
+    means2d, depths = _c(means2d), _c(depths)
+    radii = _c(radii, torch.int32)
+    T = tile_width * tile_height
+    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
+    G = lib.rs_isect_chunk_size(C, N)
+    cpc = (N + G - 1) // G
+    Tpad = (T + 1) // 2 * 2
+    order = torch.empty(C, N, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        st = _be.stream_ptr(dev)
+        _be.check(lib.rs_isect_count(_be.ptr(means2d), _be.ptr(radii), C * N, tile_width, tile_height,
+                                     _be.ptr(tiles), st), "rs_isect_count")
+        dkeys = depths.clone().view(torch.int32)              # the sort clobbers its key buffers
+        dkeys_b = torch.empty(N, device=dev, dtype=torch.int32)
+        ord_b = torch.empty(N, device=dev, dtype=torch.int32)
+        sb = lib.rs_sort_pairs_temp_bytes(N, 0, 32)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        for c in range(C):                                    # one stable argsort per camera (ties keep index order)
+            where = _be.check(lib.rs_argsort_u32(_be.ptr(dkeys[c]), _be.ptr(order[c]), _be.ptr(dkeys_b), _be.ptr(ord_b),
+                                                 N, 0, 32, _be.ptr(stemp), sb, st), "rs_argsort_u32")
+            if where == 0:
+                order[c].copy_(ord_b)
+        H = torch.empty(C * cpc, Tpad, device=dev, dtype=torch.int16)
+        tot = torch.empty(C * T, device=dev, dtype=torch.int32)
+        _be.check(lib.rs_isect_chunk_count(_be.ptr(means2d), _be.ptr(radii), _be.ptr(order), C, N, tile_width,
+                                           tile_height, G, _be.ptr(H), _be.ptr(tot), st), "rs_isect_chunk_count")
+        incl = torch.empty(C * T, device=dev, dtype=torch.int64)
+        tb = lib.rs_cumsum_temp_bytes(C * T)
+        temp = torch.empty(tb, device=dev, dtype=torch.uint8)
+        _be.check(lib.rs_cumsum_i32_i64(_be.ptr(tot), _be.ptr(incl), C * T, _be.ptr(temp), tb, st), "rs_cumsum_i32_i64")
+        base = torch.empty(C * cpc, Tpad, device=dev, dtype=torch.int32)
+        offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
+        _be.check(lib.rs_isect_chunk_base(_be.ptr(H), _be.ptr(tot), _be.ptr(incl), C, N, tile_width, tile_height, G,
+                                          _be.ptr(base), _be.ptr(offsets), st), "rs_isect_chunk_base")
+        M = int(incl[C * T - 1].item())
+        ids = torch.empty(M, device=dev, dtype=torch.int64)
+        flat = torch.empty(M, device=dev, dtype=torch.int32)
+        if M > 0:
+            _be.check(lib.rs_isect_chunk_emit(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), _be.ptr(order), C, N,
+                                              tile_width, tile_height, G, _be.ptr(base), _be.ptr(ids), _be.ptr(flat),
+                                              st), "rs_isect_chunk_emit")
+    return tiles, ids, flat, offsets
+
+
 @torch.no_grad()
 def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int,
-                            tile_height: int, method: str = "radix") -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                            tile_height: int, method: Optional[str] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go.
     -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32.
 
-    ``method="radix"`` (default): emit + onesweep radix sort + offset encode.  ``method="tile"``: the
+    ``method=None``: the module default ``ISECT_PIPELINE`` ("radix").  ``method="radix"``: emit + onesweep radix
+    sort + offset encode.  ``method="chunk"``: per-camera depth argsort + chunked counting sort (csrc/chunksort.cu).  ``method="tile"``: the
     tile-partitioned path of csrc/tilesort.cu (per-tile histogram -> offsets, atomic-slot emission into tile
     segments, per-tile shared-memory bitonic sort; falls back to radix when a tile holds more than
     ``rs_tile_sort_max_segment()`` intersections).  Both are bit-identical (tests check it); on B200 at BASELINE
@@ -291,6 +348,13 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
     and emit cost 0.35 ms, the bitonic network 0.43 ms), so it is not the default -- see DESIGN.md."""
     if tile_size != TILE_SIZE:
         raise NotImplementedError("tile_size must be 16")
+    if method is None:
+        method = ISECT_PIPELINE
+    if method == "chunk":
+        if tile_width * tile_height > _be.load().rs_isect_chunk_max_tiles() or depths.numel() == 0:
+            method = "radix"
+        else:
+            return _isect_chunked(means2d, radii, depths, tile_width, tile_height)
     if method == "radix":
         C = depths.shape[0]
         tiles, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)

@@ -46,6 +46,11 @@ _SIGNATURES = {
     "rs_isect_tile_scan": (_i, [_p, _i, _p, _p, _p, _p]),
     "rs_isect_tile_emit": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_isect_tile_sort": (_i, [_p, _p, _i, _i, _i, _ll, _i, _p, _p, _p]),
+    "rs_isect_chunk_size": (_i, [_i, _i]),
+    "rs_isect_chunk_max_tiles": (_i, []),
+    "rs_isect_chunk_count": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "rs_isect_chunk_base": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "rs_isect_chunk_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
     "rs_sort_set_items": (None, [_i]),
     "rs_sort_set_window": (None, [_i]),

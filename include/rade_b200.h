@@ -228,6 +228,25 @@ int rs_densify_stats(const float* grads /* [C,N,2] */, const int32_t* radii /* [
 int rs_project_lookup(const float* means2d /* [N,2] */, const int32_t* radii /* [N,2] */, int N, int width, int height,
                       long long* proj_flattened /* [N] */, unsigned char* valid_mask /* [N] */, void* stream);
 
+/* ---- chunked counting sort of the intersections (csrc/chunksort.cu): a sort-free path to the same isect_ids /
+ * flatten_ids / isect_offsets as isect_tiles(sort=True) + isect_offset_encode.  `order` [C][N] i32: for each camera
+ * the Gaussian indices in depth order (stable rs_argsort_u32 of that camera's depth bits).  G = entries per chunk
+ * (rs_isect_chunk_size, a multiple of 256), chunks_per_cam = ceil(N / G), Tpad = tiles rounded up to even.
+ *   rs_isect_chunk_count -> H u16 [C*chunks_per_cam][Tpad], tot i32 [C*tiles]
+ *   caller: incl = inclusive i64 scan of tot (rs_cumsum_i32_i64); M = incl[C*tiles - 1]
+ *   rs_isect_chunk_base  -> base u32 [C*chunks_per_cam][Tpad], offsets i32 [C*tiles] (= isect_offsets)
+ *   rs_isect_chunk_emit  -> isect_ids i64 [M], flatten_ids i32 [M], already sorted
+ * RS_ERR_UNSUPPORTED when tiles > rs_isect_chunk_max_tiles(): use the radix path. */
+int rs_isect_chunk_size(int C, int N);
+int rs_isect_chunk_max_tiles(void);
+int rs_isect_chunk_count(const float* means2d, const int32_t* radii, const int32_t* order, int C, int N, int tile_w,
+                         int tile_h, int G, unsigned short* H, int32_t* tot, void* stream);
+int rs_isect_chunk_base(const unsigned short* H, const int32_t* tot, const long long* incl, int C, int N, int tile_w,
+                        int tile_h, int G, unsigned int* base, int32_t* offsets, void* stream);
+int rs_isect_chunk_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order, int C,
+                        int N, int tile_w, int tile_h, int G, const unsigned int* base, long long* isect_ids,
+                        int32_t* flatten_ids, void* stream);
+
 /* ---- TSDF fusion of rendered frames on the device: replaces, in the meshing exporter
  * collab_splats/utils/mesh.py:1562-1632, the per-frame `.cpu().numpy()` + Open3D ScalableTSDFVolume.integrate (CPU).
  * Volume = hash map (64-bit packed unit coordinates, open addressing) from 16^3-voxel units to slots of a
