@@ -112,3 +112,56 @@ extern "C" int rs_fma_peak_probe(int blocks, int iters, float* out, void* stream
   fma_peak_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
   RS_RETURN_LAST_ERROR();
 }
+
+// ---- small device utilities used by the host layer in place of framework kernels
+namespace {
+struct ScaleList {
+  float* p[8];
+  long long n[8];
+  int count;
+};
+
+// x *= *g for every listed buffer, skipped altogether when *g == 1 (the usual upstream gradient of a loss): the test
+// is made on the device, so the host never reads the value
+__global__ void __launch_bounds__(256) scale_unless_one_kernel(ScaleList L, const float* __restrict__ g) {
+  const float s = __ldg(g);
+  if (s == 1.f) return;
+  const long long stride = (long long)gridDim.x * 256 * 4;
+  for (int b = 0; b < L.count; ++b) {
+    float* x = L.p[b];
+    const long long n = L.n[b], n4 = n & ~3ll;
+    for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n4; i += stride) {
+      float4 v = *reinterpret_cast<float4*>(x + i);
+      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+      *reinterpret_cast<float4*>(x + i) = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - n4)) x[n4 + threadIdx.x] *= s;
+  }
+}
+}  // namespace
+
+// In-place x_b *= *scale for up to 8 fp32 buffers (16-byte aligned), one launch; a no-op pass when *scale == 1.
+extern "C" int rs_scale_unless_one(float* const* bufs, const long long* counts, int n_bufs, const float* scale,
+                                   void* stream) {
+  RsSpan span__("rs_scale_unless_one", stream);
+  if (n_bufs < 0 || n_bufs > 8 || !scale || (n_bufs > 0 && (!bufs || !counts))) return RS_ERR_BAD_ARG;
+  if (n_bufs == 0) return RS_OK;
+  ScaleList L;
+  L.count = n_bufs;
+  for (int i = 0; i < n_bufs; ++i) {
+    if (!bufs[i] || counts[i] < 0 || ((uintptr_t)bufs[i] & 15)) return RS_ERR_BAD_ARG;
+    L.p[i] = bufs[i]; L.n[i] = counts[i];
+  }
+  scale_unless_one_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(L, scale);
+  RS_RETURN_LAST_ERROR();
+}
+
+// cudaMemsetAsync(ptr, 0, bytes) on the caller's stream (the copy-engine / driver fill, faster than a framework fill
+// kernel for the 64 MB gradient records)
+extern "C" int rs_zero_bytes(void* ptr, long long bytes, void* stream) {
+  if (bytes < 0 || (bytes > 0 && !ptr)) return RS_ERR_BAD_ARG;
+  if (bytes == 0) return RS_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  return RS_OK;
+}

@@ -536,8 +536,8 @@ class _RasterizeToPixels(torch.autograd.Function):
         v_dexp = z(v_dexp, (C, height, width, 1))
         v_dmed = z(v_dmed, (C, height, width, 1))
         v_normals = z(v_normals, (C, height, width, 3))
-        geom_grad = torch.zeros(C * N, 16, **f32)
-        color_grad = torch.zeros(rows, DP, **f32) if DP > 4 else None
+        geom_grad = _be.zeros((C * N, 16), dev)               # 64 MB at 1 M Gaussians: driver memset, not a fill kernel
+        color_grad = _be.zeros((rows, DP), dev) if DP > 4 else None
         abs_grad = torch.zeros(C * N, 2, **f32) if absgrad else None
         v_means2d = torch.empty(C, N, 2, **f32)
         v_abs = torch.empty(C, N, 2, **f32) if absgrad else None

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "rs_isect_tile_scan": (_i, [_p, _i, _p, _p, _p, _p]),
     "rs_isect_tile_emit": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_isect_tile_sort": (_i, [_p, _p, _i, _i, _i, _ll, _i, _p, _p, _p]),
+    "rs_scale_unless_one": (_i, [_p, _p, _i, _p, _p]),
+    "rs_zero_bytes": (_i, [_p, _ll, _p]),
     "rs_isect_chunk_size": (_i, [_i, _i]),
     "rs_isect_chunk_max_tiles": (_i, []),
     "rs_isect_chunk_count": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
@@ -150,6 +152,31 @@ def ptr(t):
     if not t.is_contiguous():
         raise RuntimeError("librade_b200 needs contiguous tensors")
     return C.c_void_p(t.data_ptr())
+
+
+def zeros(shape, device, dtype=torch.float32):
+    """torch.zeros through cudaMemsetAsync on the current stream (rs_zero_bytes) instead of a fill kernel."""
+    t = torch.empty(shape, device=device, dtype=dtype)
+    if t.numel():
+        with torch.cuda.device(t.device):
+            check(load().rs_zero_bytes(C.c_void_p(t.data_ptr()), t.numel() * t.element_size(), stream_ptr(t.device)),
+                  "rs_zero_bytes")
+    return t
+
+
+def scale_unless_one(tensors, scale: torch.Tensor):
+    """In place t *= scale (a device scalar) for up to 8 fp32 tensors in one launch that exits at once when
+    scale == 1 (tested on the device)."""
+    ts = [t for t in tensors if t is not None and t.numel()]
+    if not ts:
+        return
+    assert len(ts) <= 8 and all(t.dtype == torch.float32 and t.is_contiguous() for t in ts)
+    bufs = (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    counts = (C.c_longlong * len(ts))(*[t.numel() for t in ts])
+    s = scale.detach().to(torch.float32).reshape(1)
+    with torch.cuda.device(ts[0].device):
+        check(load().rs_scale_unless_one(C.cast(bufs, C.c_void_p), C.cast(counts, C.c_void_p), len(ts), ptr(s),
+                                         stream_ptr(ts[0].device)), "rs_scale_unless_one")
 
 
 def stream_ptr(device=None):

@@ -76,10 +76,18 @@ class _FusedRadeLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_terms):
-        # the kernel wrote d(loss)/d(input) for an upstream gradient of 1; scale by the real one in one
-        # multi-tensor kernel (no device->host read of its value).  Gradients w.r.t. the individual terms
-        # are not supported: differentiate the total.
-        out = torch._foreach_mul(list(ctx.saved_tensors), g_loss)
+        # the kernel wrote d(loss)/d(input) for an upstream gradient of 1; scale by the real one in place with one
+        # launch that returns immediately when it IS 1 (tested on the device: no device->host read, and no 166 MB
+        # pass in the common case).  The buffers are private to this node (a second backward through the same graph
+        # would need retain_graph and is not supported).  Gradients w.r.t. the individual terms are not supported:
+        # differentiate the total.
+        from . import backend as _be
+        if getattr(ctx, "_consumed", False):
+            raise RuntimeError("fused_rade_loss: a second backward through the same graph is not supported "
+                               "(the gradient buffers are scaled in place)")
+        ctx._consumed = True
+        out = list(ctx.saved_tensors)
+        _be.scale_unless_one(out, g_loss)
         return (*out, None, None, None, None, None, None)
 
 

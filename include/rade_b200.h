@@ -228,6 +228,13 @@ int rs_densify_stats(const float* grads /* [C,N,2] */, const int32_t* radii /* [
 int rs_project_lookup(const float* means2d /* [N,2] */, const int32_t* radii /* [N,2] */, int N, int width, int height,
                       long long* proj_flattened /* [N] */, unsigned char* valid_mask /* [N] */, void* stream);
 
+/* ---- small utilities the host layer uses in place of framework kernels.
+ * rs_scale_unless_one: in-place x_b *= *scale (device scalar) over up to 8 fp32 buffers (16-byte aligned; bufs and
+ * counts are HOST arrays); the kernel returns at once when *scale == 1 -- the upstream gradient of a loss -- without
+ * the host ever reading it.  rs_zero_bytes: cudaMemsetAsync on the caller's stream. */
+int rs_scale_unless_one(float* const* bufs, const long long* counts, int n_bufs, const float* scale, void* stream);
+int rs_zero_bytes(void* ptr, long long bytes, void* stream);
+
 /* ---- chunked counting sort of the intersections (csrc/chunksort.cu): a sort-free path to the same isect_ids /
  * flatten_ids / isect_offsets as isect_tiles(sort=True) + isect_offset_encode.  `order` [C][N] i32: for each camera
  * the Gaussian indices in depth order (stable rs_argsort_u32 of that camera's depth bits).  G = entries per chunk
