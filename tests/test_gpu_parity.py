@@ -512,6 +512,45 @@ def test_full_size_properties(cuda_dev):
     assert bool((meta["radii"].reshape(-1, 2)[meta["flatten_ids"].long()] > 0).all())
 
 
+@pytest.mark.parametrize("cfg_id,win", [(2, (31, 37, 57, 63)), (3, (14, 20, 27, 33))])
+def test_full_size_window_matches_oracle(cuda_dev, cfg_id, win):
+    """BASELINE configs 2 and 3 at FULL size (1 M Gaussians, 1920x1080, sh3; 500 k Gaussians with 3 + 64 feature
+    channels, 960x540; RGB+ED antialiased) against the oracle: the
+    oracle projects, intersects and sorts everything (so radii, tile counts, the 6.9 M sorted 64-bit keys, flatten ids
+    and the 8160 tile offsets are compared bit for bit) and composites a 6x6-tile window in the image centre, where
+    images and -- for a loss over that window -- the gradients of all five inputs are compared."""
+    from gsplat.rendering import rasterization
+    cfg = scenes.BASELINE_CONFIGS[cfg_id]
+    gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
+    sh = 3 if cfg_id == 2 else None
+    params = scenes.activate(gs, sh)
+    W, H = cfg.width, cfg.height
+    y0, y1, x0, x1 = win[0] * 16, win[1] * 16, win[2] * 16, win[3] * 16    # win = tile rows / tile columns
+    cpu = [t.detach().clone().requires_grad_(True) for t in params]
+    ref = O.rasterization(*cpu, vm, Ks, W, H, sh_degree=sh, render_mode="RGB+ED", rasterize_mode="antialiased",
+                          return_depth_normal=True, return_aux=True, tile_window=win)
+    gpu = _gpu(params, cuda_dev, grad=True)
+    got = rasterization(*gpu, vm.to(cuda_dev), Ks.to(cuda_dev), W, H, packed=False, sh_degree=sh, render_mode="RGB+ED",
+                        rasterize_mode="antialiased", return_depth_normal=True)
+    meta, rmeta = got[5], ref[5]
+    assert rmeta["isect_ids"].numel() > 1_000_000 and got[0].shape[-1] == (4 if cfg_id == 2 else 68)
+    for key in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(meta[key].cpu(), rmeta[key]), f"meta[{key}] differs at full size"
+    keep = ~rmeta["fragile"][:, y0:y1, x0:x1]
+    assert float(ref[1][0, y0:y1, x0:x1].detach().mean()) > 0.5 and int((~keep).sum()) < keep.numel() // 20
+    for i, nm in enumerate(["render", "alpha", "expected_depths", "median_depths", "expected_normals"]):
+        ok, msg = close_report(nm, got[i][:, y0:y1, x0:x1], ref[i][:, y0:y1, x0:x1], mask=keep)
+        assert ok, msg
+    g = torch.Generator().manual_seed(4)
+    ws = [torch.randn(1, y1 - y0, x1 - x0, t.shape[-1], generator=g) * keep[..., None] for t in ref[:5]]
+    sum((t[:, y0:y1, x0:x1] * w).sum() for t, w in zip(ref[:5], ws)).backward()
+    sum((t[:, y0:y1, x0:x1] * w.to(cuda_dev)).sum() for t, w in zip(got[:5], ws)).backward()
+    for nm, a, b in zip(("means", "quats", "scales", "opacities", "sh_coeffs"), gpu, cpu):
+        ok, msg = grad_close_report("v_" + nm, a.grad, b.grad, rel=3e-3)
+        assert ok, msg
+        assert float(b.grad.abs().max()) > 0
+
+
 # ------------------------------------------------------------------------------------------------ fused loss (8f row f1)
 @pytest.mark.parametrize("use_dn,with_bg,D", [(True, False, 4), (True, True, 3), (False, False, 3)])
 def test_fused_loss_matches_reference_glue(cuda_dev, use_dn, with_bg, D):
