@@ -618,6 +618,82 @@ __device__ __forceinline__ void commit_color_grads(const float (&v_c)[DP], float
   }
 }
 
+// ---- tensor-core reduction of the wide colour gradients (rade-features rows, DP >= 32)
+// The per-Gaussian colour gradient is a small dense contraction over the warp's 32 pixels,
+//     v_col[g][ch] = sum_p vis[p][g] * v_c[p][ch],
+// the one piece of the compositing backward that is GEMM-shaped: M = channels (16-row tiles), N = 8 pending
+// Gaussians, K = 32 pixels.  A warp parks the visibilities of the Gaussians it blends (8 x 32 floats) and every 8th
+// one contracts them against its v_c rows (already in shared memory) with mma.sync m16n8k8 TF32 instructions.  Both
+// operands are split into a TF32 head and a TF32 tail (x = hi + lo) and the three significant partial products are
+// accumulated in fp32 ("3xTF32"), so the result keeps fp32 accuracy (the dropped lo*lo term is ~2^-22 relative).
+// The C fragments land as (channel, Gaussian) pairs and are committed with one RED each, 8 consecutive channels per
+// quarter-warp.  Replaces ~11 issue slots per contributing pixel and Gaussian of the shuffle/row-walk formulation.
+__device__ __forceinline__ unsigned tf32_hi(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+  hi = tf32_hi(x);
+  lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int CM_PEND = 8;      // Gaussians parked per warp before a contraction
+constexpr int CM_VSTRIDE = 36;  // row stride of the parked visibilities (conflict-free B-fragment loads)
+
+// vc_w: the warp's v_c rows [32][DP]; vis_w: parked visibilities [CM_PEND][CM_VSTRIDE]; row_w: colour rows [CM_PEND]
+template <int DP>
+__device__ __forceinline__ void flush_color_mma(const float* __restrict__ vc_w, const float* __restrict__ vis_w,
+                                                const int* __restrict__ row_w, int np, float* __restrict__ color_grad,
+                                                int D, int lane) {
+  constexpr int MT = (DP + 15) / 16;
+  const int gid = lane >> 2, tig = lane & 3;
+  float c[MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) c[mt][0] = c[mt][1] = c[mt][2] = c[mt][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    unsigned b0h, b0l, b1h, b1l;
+    tf32_split(vis_w[gid * CM_VSTRIDE + tig + 8 * ks], b0h, b0l);
+    tf32_split(vis_w[gid * CM_VSTRIDE + tig + 4 + 8 * ks], b1h, b1l);
+    const float* r0 = vc_w + (tig + 8 * ks) * DP;
+    const float* r1 = r0 + 4 * DP;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      // rows past DP only feed C rows that are never committed; clamp them into the row to stay inside the array
+      const int ch0 = min(gid + 16 * mt, DP - 1), ch1 = min(gid + 8 + 16 * mt, DP - 1);
+      unsigned ah[4], al[4];
+      tf32_split(r0[ch0], ah[0], al[0]);
+      tf32_split(r0[ch1], ah[1], al[1]);
+      tf32_split(r1[ch0], ah[2], al[2]);
+      tf32_split(r1[ch1], ah[3], al[3]);
+      mma_tf32_16x8x8(c[mt], al, b0h, b1h);
+      mma_tf32_16x8x8(c[mt], ah, b0l, b1l);
+      mma_tf32_16x8x8(c[mt], ah, b0h, b1h);
+    }
+  }
+  const int g0 = 2 * tig, g1 = g0 + 1;
+  float* d0 = color_grad + (size_t)row_w[g0] * DP;
+  float* d1 = color_grad + (size_t)row_w[g1] * DP;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    const int ch = gid + 16 * mt;
+    if (ch < D) {
+      if (g0 < np) atomicAdd(d0 + ch, c[mt][0]);
+      if (g1 < np) atomicAdd(d1 + ch, c[mt][1]);
+    }
+    if (ch + 8 < D) {
+      if (g0 < np) atomicAdd(d0 + ch + 8, c[mt][2]);
+      if (g1 < np) atomicAdd(d1 + ch + 8, c[mt][3]);
+    }
+  }
+}
+
 // The median depth of a pixel is the ray distance t = ray_t + ray_plane . d of ONE Gaussian (median_ids): its
 // gradient is three scalar atomics per pixel, issued once here instead of a compare + select per blended pair in
 // the compositing loop.
@@ -631,8 +707,8 @@ __device__ __forceinline__ void commit_median_grad(const RasterArgs& a, int med_
   atomicAdd(rec + 8, v_dmed * (q0.y - py));
 }
 
-template <int DP, int BATCH, bool ABSGRAD>
-__global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
+template <int DP, int BATCH, bool ABSGRAD, bool CMMA>
+__global__ void __launch_bounds__(RT, (CMMA ? 2 : 1)) rasterize_bwd_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -662,7 +738,12 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
   // is broadcast by one shuffle, v_c[p][.] is read from shared memory (conflict free) and the totals land one channel
   // per lane, i.e. as coalesced REDs -- instead of 31 shuffle exchanges per 32 channels with lanes = pixels.
   constexpr bool CHLANE = DP >= 32;
+  static_assert(!CMMA || CHLANE, "the tensor-core colour reduction is for wide rows");
   float* s_vc = reinterpret_cast<float*>(smem_raw + sizeof(Smem<DP, BATCH>));   // [RT][DP], CHLANE only
+  // CMMA: per-warp parking lot of the tensor-core colour reduction (flush_color_mma)
+  float* cm_vis = s_vc + RT * DP + warp * (CM_PEND * CM_VSTRIDE);               // [CM_PEND][CM_VSTRIDE]
+  int* cm_row = reinterpret_cast<int*>(s_vc + RT * DP + (RT / 32) * (CM_PEND * CM_VSTRIDE)) + warp * CM_PEND;
+  int cm_n = 0;
   if constexpr (CHLANE) {
 #pragma unroll
     for (int k = 0; k < DP; ++k) s_vc[t * DP + k] = v_c[k];   // (after the ED rescale above; made visible by the barrier below)
@@ -788,7 +869,16 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
         }
         if constexpr (DP > 4) {
           const int row = a.color_per_cam ? id : id % a.N;
-          if constexpr (CHLANE) {
+          if constexpr (CMMA) {
+            cm_vis[cm_n * CM_VSTRIDE + lane] = vis;
+            if (lane == 0) cm_row[cm_n] = row;
+            if (++cm_n == CM_PEND) {
+              __syncwarp();
+              flush_color_mma<DP>(s_vc + (size_t)(warp * 32) * DP, cm_vis, cm_row, CM_PEND, a.color_grad, a.D, lane);
+              __syncwarp();
+              cm_n = 0;
+            }
+          } else if constexpr (CHLANE) {
             constexpr int NCH = (DP + 31) / 32;
             float acc[NCH];
 #pragma unroll
@@ -831,6 +921,16 @@ __global__ void __launch_bounds__(RT) rasterize_bwd_kernel(const RasterArgs a) {
     if (b >= 2 && t < BATCH) s.ids[b & 1][t] = next_id;
   }
   rs::cp_async_wait_all();
+  if constexpr (CMMA) {
+    if (cm_n > 0) {   // contract what is still parked (warp-uniform); unused slots count as zero visibility
+      for (int g = cm_n; g < CM_PEND; ++g) {
+        cm_vis[g * CM_VSTRIDE + lane] = 0.f;
+        if (lane == 0) cm_row[g] = 0;
+      }
+      __syncwarp();
+      flush_color_mma<DP>(s_vc + (size_t)(warp * 32) * DP, cm_vis, cm_row, cm_n, a.color_grad, a.D, lane);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ backward, 2 px/lane
@@ -1089,14 +1189,23 @@ static int g_cull_mode = 1;  // 0: bbox of the footprint ellipse; 1 (default): e
 // are halved there to keep two CTAs per SM
 template <int DP> struct BwdBatch { static constexpr int value = DP >= 64 ? 32 : Batch<DP>::value; };
 
-template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
+static int g_color_mma = 1;   // wide rows: 1 = tensor-core colour-gradient reduction (3xTF32), 0 = shuffle / row-walk
+
+template <int DP, bool ABSGRAD, bool CMMA> int launch_bwd3(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = BwdBatch<DP>::value;
-  const size_t smem = sizeof(Smem<DP, B>) + (DP >= 32 ? sizeof(float) * RT * DP : 0);
-  cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B, ABSGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  const size_t smem = sizeof(Smem<DP, B>) + (DP >= 32 ? sizeof(float) * RT * DP : 0) +
+                      (CMMA ? (RT / 32) * (sizeof(float) * CM_PEND * CM_VSTRIDE + sizeof(int) * CM_PEND) : 0);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B, ABSGRAD, CMMA>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
-  rasterize_bwd_kernel<DP, B, ABSGRAD><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  rasterize_bwd_kernel<DP, B, ABSGRAD, CMMA><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
+}
+template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
+  if constexpr (DP >= 32) {
+    if (g_color_mma) return launch_bwd3<DP, ABSGRAD, true>(a, st);
+  }
+  return launch_bwd3<DP, ABSGRAD, false>(a, st);
 }
 template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
@@ -1136,6 +1245,8 @@ extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 // tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
 extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
 extern "C" int rs_raster_get_variant(void) { return g_raster_variant; }
+// wide colour rows (>= 32 channels): 1 (default) = tensor-core colour-gradient reduction, 0 = SIMT row walk
+extern "C" void rs_raster_set_color_mma(int on) { g_color_mma = on ? 1 : 0; }
 extern "C" void rs_raster_set_occupancy(int min_blocks) { g_bwd2_minb = (min_blocks == 6 || min_blocks == 7) ? min_blocks : 4; }
 // footprint test used by rs_pack_geom AND the compositing kernels (set it before rs_pack_geom and leave it until
 // the backward has run): 0 = padded bbox of the alpha >= 1/255 ellipse, 1 (default) = exact ellipse-vs-rectangle

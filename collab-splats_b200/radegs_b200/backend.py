@@ -61,6 +61,7 @@ _SIGNATURES = {
     "rs_raster_set_stats": (None, [_p]),
     "rs_raster_set_variant": (None, [_i]),
     "rs_raster_get_variant": (_i, []),
+    "rs_raster_set_color_mma": (None, [_i]),
     "rs_raster_set_occupancy": (None, [_i]),
     "rs_raster_set_cull_mode": (None, [_i]),
     "rs_raster_get_cull_mode": (_i, []),

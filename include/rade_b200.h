@@ -136,6 +136,9 @@ void rs_raster_set_stats(unsigned long long* dev_counters);
  * backward has run): 0 = one pixel per lane (8x4 block per warp), 1 = two pixels per lane (8x8 block per warp) */
 void rs_raster_set_variant(int variant);
 int rs_raster_get_variant(void);
+/* wide colour rows (>= 32 channels): 1 (default) = colour gradients reduced on the tensor cores (mma.sync TF32 with
+ * head/tail operand splitting, fp32-accurate), 0 = SIMT row walk.  A/B knob. */
+void rs_raster_set_color_mma(int on);
 void rs_raster_set_occupancy(int min_blocks); /* tuning knob: register cap of the 2-px backward (4, 6 or 7 CTAs/SM) */
 /* footprint (alpha >= 1/255) test the records are packed for and the kernels apply per (warp, Gaussian): 0 = padded
  * bbox of the footprint ellipse, 1 (default) = exact ellipse-vs-rectangle test.  Both are conservative, so results
