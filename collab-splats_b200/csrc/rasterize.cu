@@ -272,6 +272,218 @@ __device__ __forceinline__ float inv_ray_len(const RasterArgs& a, int cam, float
   return 1.0f / sqrtf(rx * rx + ry * ry + 1.0f);
 }
 
+// ---- TF32 tensor-core helpers for the wide (rade-features) colour rows: mma.sync m16n8k8 with both operands split
+// into a TF32 head and tail (x = hi + lo); the three significant partial products are accumulated in fp32
+// ("3xTF32": the dropped lo*lo term is ~2^-22 relative), so the blends keep fp32 accuracy.
+__device__ __forceinline__ unsigned tf32_hi(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
+  hi = tf32_hi(x);
+  lo = tf32_hi(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int CM_PEND = 8;      // Gaussians parked per warp before a contraction
+constexpr int CM_VSTRIDE = 36;  // row stride of the parked visibilities (conflict-free B-fragment loads)
+
+
+// ------------------------------------------------------------------------------------------------ forward, wide rows
+// Forward for DP >= 32 with the colour blend on the tensor cores.  The blend of a warp's 32 pixels with 8 Gaussians,
+//     out[p][ch] += sum_g vis[p][g] * colour[g][ch],
+// is M = 32 pixels (two 16-row tiles) x N = DP channels (8-column tiles) x K = 8 Gaussians: the warp parks the
+// visibilities of the Gaussians it blends (and their slot in the staged batch) and contracts every 8th one -- or what
+// is parked when the batch ends, since the staged colour rows are recycled -- against the colour rows in shared
+// memory.  The DP accumulators per pixel become C fragments (each lane holds 4 pixels x DP/4 channels).  Everything
+// else (alpha test, transmittance, depth / normal / median bookkeeping, early termination) is as in
+// rasterize_fwd_kernel, written branch-free so that a skipped pair is an exact no-op.
+template <int DP>
+__device__ __forceinline__ void flush_blend_mma(float (&cf)[2][(DP + 7) / 8][4], const float* __restrict__ vis_w,
+                                                const int* __restrict__ slot_w, const float (*col)[DP], int lane) {
+  constexpr int NT = (DP + 7) / 8;
+  const int gid = lane >> 2, tig = lane & 3;
+  unsigned ah[2][4], al[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    tf32_split(vis_w[tig * CM_VSTRIDE + gid + 16 * mt], ah[mt][0], al[mt][0]);
+    tf32_split(vis_w[tig * CM_VSTRIDE + gid + 8 + 16 * mt], ah[mt][1], al[mt][1]);
+    tf32_split(vis_w[(tig + 4) * CM_VSTRIDE + gid + 16 * mt], ah[mt][2], al[mt][2]);
+    tf32_split(vis_w[(tig + 4) * CM_VSTRIDE + gid + 8 + 16 * mt], ah[mt][3], al[mt][3]);
+  }
+  const float* c0 = col[slot_w[tig]];
+  const float* c1 = col[slot_w[tig + 4]];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int ch = min(gid + 8 * nt, DP - 1);   // columns past DP are never written out
+    unsigned b0h, b0l, b1h, b1l;
+    tf32_split(c0[ch], b0h, b0l);
+    tf32_split(c1[ch], b1h, b1l);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      mma_tf32_16x8x8(cf[mt][nt], al[mt], b0h, b1h);
+      mma_tf32_16x8x8(cf[mt][nt], ah[mt], b0l, b1l);
+      mma_tf32_16x8x8(cf[mt][nt], ah[mt], b0h, b1h);
+    }
+  }
+}
+
+template <int DP, int BATCH>
+__global__ void __launch_bounds__(RT, 2) rasterize_fwd_mma_kernel(const RasterArgs a) {
+  constexpr int NT = (DP + 7) / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float* cm_vis = reinterpret_cast<float*>(smem_raw + sizeof(Smem<DP, BATCH>)) + warp * (CM_PEND * CM_VSTRIDE);
+  int* cm_slot = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw + sizeof(Smem<DP, BATCH>)) +
+                                        (RT / 32) * (CM_PEND * CM_VSTRIDE)) + warp * CM_PEND;
+  const TileCtx c = tile_ctx(a, lane, warp);
+  const int start = c.start, end = c.end;
+  const float px = c.px, py = c.py;
+
+  float T = c.inside ? 1.f : 0.f, T_out = 1.f, dsum = 0.f, tmed = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  float cf[2][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) cf[mt][nt][0] = cf[mt][nt][1] = cf[mt][nt][2] = cf[mt][nt][3] = 0.f;
+  int last_id = start - 1, med_id = -1, cm_n = 0;
+
+  const int nb = (end - start + BATCH - 1) / BATCH;
+  if (nb > 0) {
+    if (t < BATCH) { const int i = start + t; s.ids[0][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH>(s, 0, min(BATCH, end - start), a, t);
+    if (nb > 1 && t < BATCH) { const int i = start + BATCH + t; s.ids[1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+  }
+  bool warp_done = !__any_sync(RS_FULL_MASK, T != 0.f);
+  for (int b = 0; b < nb; ++b) {
+    rs::cp_async_wait_all();
+    if (__syncthreads_count(T != 0.f) == 0) break;
+    int next_id = 0;
+    if (b + 1 < nb) {
+      issue_gather<DP, BATCH>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
+      if (b + 2 < nb && t < BATCH) {
+        const int i = start + (b + 2) * BATCH + t;
+        next_id = i < end ? __ldg(a.flatten_ids + i) : 0;
+      }
+    }
+    if (!warp_done) {
+      const int buf = b & 1;
+      const int base_idx = start + b * BATCH;
+      const int bcount = min(BATCH, end - base_idx);
+      for (int g0 = 0; g0 < bcount; g0 += 32) {
+        const int j = g0 + lane;
+        bool hit = false;
+        if (j < bcount) hit = footprint_hit(s, buf, j, a.exact_cull != 0, c.rcx, c.rcy, 3.5f, 1.5f);
+        unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+        while (m) {
+          const int jj = g0 + __ffs(m) - 1;
+          m &= m - 1;
+          const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
+          const float dx = q0.x - px, dy = q0.y - py;
+          const float sig = q1.x * dx * dx + q1.z * dy * dy + q1.y * dx * dy;
+          const float alpha = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
+          const bool ok = sig >= 0.f && alpha >= RS_ALPHA_MIN;
+          if (!__any_sync(RS_FULL_MASK, ok)) continue;
+          // branch-free: a failed pair acts as alpha = 0, a dead pixel (T == 0) discards its update
+          const float am = ok ? alpha : 0.f;
+          const float nT = T * (1.f - am);
+          const bool live = nT > RS_T_STOP;              // false for dead pixels and for the terminating pair
+          T_out = (!live && T != 0.f) ? T : T_out;
+          const float vis = live ? am * T : 0.f;
+          if (__any_sync(RS_FULL_MASK, vis != 0.f)) {
+            const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+            const float tt = q2.x + q2.y * dx + q2.z * dy;
+            dsum += vis * tt;
+            nx += vis * q3.x; ny += vis * q3.y; nz += vis * q3.z;
+#if RS_MEDIAN_INCLUSIVE
+            const bool med = live && T > 0.5f && nT <= 0.5f;
+#else
+            const bool med = live && T > 0.5f && nT < 0.5f;
+#endif
+            tmed = med ? tt : tmed;
+            med_id = med ? base_idx + jj : med_id;
+            last_id = (live && ok) ? base_idx + jj : last_id;
+            cm_vis[cm_n * CM_VSTRIDE + lane] = vis;
+            if (lane == 0) cm_slot[cm_n] = jj;
+            if (++cm_n == CM_PEND) {
+              __syncwarp();
+              flush_blend_mma<DP>(cf, cm_vis, cm_slot, s.col[buf], lane);
+              __syncwarp();
+              cm_n = 0;
+            }
+          }
+          T = live ? nT : 0.f;
+        }
+        if (!__any_sync(RS_FULL_MASK, T != 0.f)) { warp_done = true; break; }
+      }
+      if (cm_n > 0) {   // the staged colour rows of this batch are about to be recycled: contract what is parked
+        for (int g = cm_n; g < CM_PEND; ++g) {
+          cm_vis[g * CM_VSTRIDE + lane] = 0.f;
+          if (lane == 0) cm_slot[g] = 0;
+        }
+        __syncwarp();
+        flush_blend_mma<DP>(cf, cm_vis, cm_slot, s.col[buf], lane);
+        __syncwarp();
+        cm_n = 0;
+      }
+    }
+    if (b + 2 < nb && t < BATCH) s.ids[b & 1][t] = next_id;
+  }
+  rs::cp_async_wait_all();
+
+  if (T == 0.f) T = T_out;   // (outside pixels: T_out = 1)
+  // colours: the C fragments hold, per lane, pixels gid + 8h (h = 0..3) of the warp's 8x4 block and channels
+  // 2 tig + 8 nt (+1); the per-pixel transmittance comes from the lane that owns the pixel
+  {
+    const int gid = lane >> 2, tig = lane & 3;
+    const float* bg = a.backgrounds ? a.backgrounds + (size_t)c.cam * a.D : nullptr;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int mp = gid + 8 * h;
+      const float Tm = __shfl_sync(RS_FULL_MASK, T, mp);
+      const int pxm = c.x0 + (mp & 7), pym = c.y0 + (mp >> 3);
+      if (pxm < a.W && pym < a.H) {
+        float* oc = a.out_colors + (((size_t)c.cam * a.H + pym) * a.W + pxm) * a.D;
+        const float ed_scale = 1.f / fmaxf(1.f - Tm, 1e-10f);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int ch = 2 * tig + 8 * nt + e;
+            if (ch < a.D) {
+              float v = cf[h >> 1][nt][(h & 1) * 2 + e] + (bg ? Tm * __ldg(bg + ch) : 0.f);
+              v *= (ch == a.ed_channel) ? ed_scale : 1.f;
+              oc[ch] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (c.inside) {
+    const size_t pix = ((size_t)c.cam * a.H + c.pyi) * a.W + c.pxi;
+    const float il = inv_ray_len(a, c.cam, px, py);
+    a.out_alphas[pix] = 1.f - T;
+    a.out_T[pix] = T;
+#if RS_NORMALIZE_EXPECTED_DEPTH
+    a.out_dexp[pix] = dsum * il / fmaxf(1.f - T, 1e-10f);
+#else
+    a.out_dexp[pix] = dsum * il;
+#endif
+    a.out_dmed[pix] = tmed * il;
+    a.out_normals[pix * 3] = nx; a.out_normals[pix * 3 + 1] = ny; a.out_normals[pix * 3 + 2] = nz;
+    a.last_ids[pix] = last_id;
+    a.median_ids[pix] = med_id;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int DP, int BATCH, bool STATS>
 __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const RasterArgs a) {
@@ -628,24 +840,6 @@ __device__ __forceinline__ void commit_color_grads(const float (&v_c)[DP], float
 // accumulated in fp32 ("3xTF32"), so the result keeps fp32 accuracy (the dropped lo*lo term is ~2^-22 relative).
 // The C fragments land as (channel, Gaussian) pairs and are committed with one RED each, 8 consecutive channels per
 // quarter-warp.  Replaces ~11 issue slots per contributing pixel and Gaussian of the shuffle/row-walk formulation.
-__device__ __forceinline__ unsigned tf32_hi(float x) {
-  unsigned r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void tf32_split(float x, unsigned& hi, unsigned& lo) {
-  hi = tf32_hi(x);
-  lo = tf32_hi(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int CM_PEND = 8;      // Gaussians parked per warp before a contraction
-constexpr int CM_VSTRIDE = 36;  // row stride of the parked visibilities (conflict-free B-fragment loads)
-
 // vc_w: the warp's v_c rows [32][DP]; vis_w: parked visibilities [CM_PEND][CM_VSTRIDE]; row_w: colour rows [CM_PEND]
 template <int DP>
 __device__ __forceinline__ void flush_color_mma(const float* __restrict__ vc_w, const float* __restrict__ vis_w,
@@ -1169,7 +1363,22 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
 static int g_bwd2_minb = 4;   // tuning knob (rs_raster_set_occupancy): register cap of the 2-px backward
 static int g_raster_variant = 1;  // DP == 4 only.  0: one pixel per lane (8x4 per warp); 1 (default): two pixels per lane (8x8 per warp)
 
+static int g_color_mma = 1;   // wide rows: 1 = tensor-core colour blend / colour-gradient reduction (3xTF32), 0 = SIMT
+
+template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
+  constexpr int B = Batch<DP>::value;
+  const size_t smem = sizeof(Smem<DP, B>) + (RT / 32) * (sizeof(float) * CM_PEND * CM_VSTRIDE + sizeof(int) * CM_PEND);
+  cudaError_t e = cudaFuncSetAttribute(rasterize_fwd_mma_kernel<DP, B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  rasterize_fwd_mma_kernel<DP, B><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
+  RS_RETURN_LAST_ERROR();
+}
+
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
+  if constexpr (DP >= 64) {   // narrower rows: the C fragments cost more registers than the blend saves
+    if (g_color_mma && !a.stats) return launch_fwd_mma<DP>(a, st);
+  }
   if constexpr (DP == 4) {
     if (g_raster_variant == 1) {
       constexpr int B2 = 128;
@@ -1188,8 +1397,6 @@ static int g_cull_mode = 1;  // 0: bbox of the footprint ellipse; 1 (default): e
 // backward batch: wide rows also keep the tile's v_c rows (RT x DP floats) in shared memory, so the staged batches
 // are halved there to keep two CTAs per SM
 template <int DP> struct BwdBatch { static constexpr int value = DP >= 64 ? 32 : Batch<DP>::value; };
-
-static int g_color_mma = 1;   // wide rows: 1 = tensor-core colour-gradient reduction (3xTF32), 0 = shuffle / row-walk
 
 template <int DP, bool ABSGRAD, bool CMMA> int launch_bwd3(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = BwdBatch<DP>::value;

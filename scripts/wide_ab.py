@@ -11,11 +11,13 @@ from gsplat.rendering import rasterization
 dev = torch.device("cuda:0")
 lib = be.load()
 cfg = scenes.BASELINE_CONFIGS[3]
-gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
+NF = int(sys.argv[1]) if len(sys.argv) > 1 else 64          # feature channels (config 3: 64 -> 3 + 64 + 1 = 68 rows)
+gs = scenes.make_gaussians(cfg.n_gaussians, None, NF, cfg.seed)
+vm, Ks = scenes.make_cameras(1, cfg.width, cfg.height, cfg.seed)
 p = [t.to(dev).requires_grad_(True) for t in scenes.activate(gs, None)]
 vmd, Kd = vm.to(dev), Ks.to(dev)
 torch.manual_seed(0)
-w = torch.randn(1, cfg.height, cfg.width, 68, device=dev)
+w = torch.randn(1, cfg.height, cfg.width, 3 + NF + 1, device=dev)
 
 
 def step():
@@ -25,7 +27,7 @@ def step():
     ((o[0] * w).sum() + o[2].mean() + o[3].mean() + o[4].mean()).backward()
 
 
-out = {}
+out = {"channels": 3 + NF + 1}
 grads = {}
 for mode in (0, 1, 0, 1):
     lib.rs_raster_set_color_mma(mode)

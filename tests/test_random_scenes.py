@@ -36,7 +36,7 @@ def test_random_tiny_scenes_match_oracle(cuda_dev, p):
     vm, Ks = scenes.make_cameras(p["views"], p["w"], p["h"], p["seed"], radius=p["radius"])
     gs["log_scales"] = gs["log_scales"] + p["boost"]
     if p["flat_axis"]:
-        gs["log_scales"][:, 2] = -12.0                             # degenerate (disc-like) Gaussians
+        gs["log_scales"][:, 2] = -9.0                              # degenerate (disc-like) Gaussians, 1.2e-4 thick
     params = scenes.activate(gs, sh)
     W, H, C = p["w"], p["h"], p["views"]
     g = torch.Generator().manual_seed(p["seed"])
@@ -65,8 +65,8 @@ def test_random_tiny_scenes_match_oracle(cuda_dev, p):
         loss_ref.backward()
     else:                                  # nothing visible: the oracle returns constants, the gradients must be zero
         assert rmeta["isect_ids"].numel() == 0
-    # exp(-12)-thin discs are ill-conditioned in fp32 (Sigma^-1 holds 2.6e10): the fp64 oracle sits between the fp32
-    # oracle and the kernel, each ~0.5 % off for the thin axis -- the geometry gradients get a looser bound there
+    # thin discs are ill-conditioned in fp32 (Sigma^-1 holds 1/thickness^2 ~ 7e7; at exp(-12) the fp64 oracle sits
+    # between the fp32 oracle and the kernel, each ~0.5-1 % off for the thin axis): looser geometry bound there
     rel_geo = 2e-2 if p["flat_axis"] else 3e-3
     for nm, a, b in zip(("means", "quats", "scales", "opacities", "colors"), gpu, cpu):
         ok, msg = grad_close_report("v_" + nm, a.grad, b.grad, rel=rel_geo if nm in ("means", "quats", "scales") else 3e-3,
