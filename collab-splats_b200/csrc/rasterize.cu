@@ -902,7 +902,7 @@ __device__ __forceinline__ void commit_median_grad(const RasterArgs& a, int med_
 }
 
 template <int DP, int BATCH, bool ABSGRAD, bool CMMA>
-__global__ void __launch_bounds__(RT, (CMMA ? 2 : 1)) rasterize_bwd_kernel(const RasterArgs a) {
+__global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const RasterArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
