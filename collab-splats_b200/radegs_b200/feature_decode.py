@@ -126,11 +126,12 @@ class TwoLayerMLP(nn.Module):
         return w1, self.hidden_conv.bias, {k: (c.weight.view(c.out_channels, -1), c.bias)
                                            for k, c in self.feature_branch_dict.items()}
 
-    @torch.no_grad()
     def forward(self, x: Tensor) -> Dict[str, Tensor]:
-        """[1,F,H,W] -> {branch: [1,C,H,W]} (inference; training goes through ``features_loss``)."""
+        """[1,F,H,W] -> {branch: [1,C,H,W]} (inference; training goes through ``features_loss``, and a call that
+        would need gradients raises)."""
         if x.dim() != 4 or x.shape[0] != 1:
             raise ValueError("TwoLayerMLP.forward takes a [1,F,H,W] map")
+        _refuse_autograd("TwoLayerMLP.forward", x, self)
         _, F, H, W = x.shape
         hwf = x[0].permute(1, 2, 0).contiguous()
         out = decode_features(hwf, self, {k: (c.out_channels, H, W) for k, c in self.feature_branch_dict.items()},
@@ -147,12 +148,26 @@ class TwoLayerMLP(nn.Module):
         return {k: v.view(v.shape[0], N).t() for k, v in out.items()}
 
 
-@torch.no_grad()
+def _refuse_autograd(what: str, render: Tensor, decoder: "TwoLayerMLP"):
+    if torch.is_grad_enabled() and (render.requires_grad or any(p.requires_grad for p in decoder.parameters())):
+        raise NotImplementedError(
+            f"{what} is the inference path (the reference calls it under no_grad in get_outputs_for_camera, "
+            "rade_features_model.py:509-511) and would silently drop gradients here; for training use "
+            "radegs_b200.feature_decode.features_loss, or call it under torch.no_grad()")
+
+
 def decode_features(render: Tensor, decoder: TwoLayerMLP, feature_dims: Dict[str, Sequence[int]], main: str,
                     resize_factor: float = 1.0, ch0: int = 0, n_features: Optional[int] = None) -> Dict[str, Tensor]:
     """rade_features_model.py:149-189: rendered features [H,W,F] (or the whole colour output with ``ch0`` /
     ``n_features`` selecting the feature columns) -> {branch: [C_b, H_b, W_b]}; the main branch at
-    ``int(dims * resize_factor)``, every other branch at its own feature-map size."""
+    ``int(dims * resize_factor)``, every other branch at its own feature-map size.  Inference only: with gradients
+    enabled and differentiable inputs it raises instead of returning tensors that are cut off from the graph."""
+    _refuse_autograd("decode_features", render, decoder)
+    with torch.no_grad():
+        return _decode_features(render, decoder, feature_dims, main, resize_factor, ch0, n_features)
+
+
+def _decode_features(render, decoder, feature_dims, main, resize_factor, ch0, n_features):
     w1, b1, branches = decoder._flat()
     F = n_features if n_features is not None else render.shape[-1] - ch0
     _validate(render, ch0, F, w1)

@@ -94,7 +94,10 @@ def test_cuda_matches_golden_from_reference_decoder(cuda_dev):
     render = torch.zeros(H, W, 3 + F + 1)
     render[..., 3:3 + F] = g["features"]
     render = render.to(cuda_dev).requires_grad_(True)
-    out = fd.decode_features(render, dec, DIMS, "clip", ch0=3, n_features=F)
+    with pytest.raises(NotImplementedError, match="features_loss"):     # would silently cut the graph: refused
+        fd.decode_features(render, dec, DIMS, "clip", ch0=3, n_features=F)
+    with torch.no_grad():
+        out = fd.decode_features(render, dec, DIMS, "clip", ch0=3, n_features=F)
     for k in DIMS:
         torch.testing.assert_close(out[k].cpu(), g[f"decoded_{k}"], atol=1e-5, rtol=1e-4)
     loss = fd.features_loss(render, dec, DIMS, "clip", {k: g[f"gt_{k}"].to(cuda_dev) for k in DIMS}, ch0=3,
@@ -134,7 +137,8 @@ def test_cuda_matches_oracle(cuda_dev, Fin, Hd, H, W, dims, main):
     ref_loss = fo.features_loss(cf, cw1, cb1, cbr, dims, main, gt, reg_lambda=0.25, loss_lambda=0.5)
     ref_loss.backward()
     df = feats.to(cuda_dev).requires_grad_(True)
-    out = fd.decode_features(df, dec, dims, main)
+    with torch.no_grad():
+        out = fd.decode_features(df, dec, dims, main)
     for k in dims:
         torch.testing.assert_close(out[k].cpu(), ref_dec[k].detach(), atol=1e-5, rtol=1e-4)
     loss = fd.features_loss(df, dec, dims, main, {k: v.to(cuda_dev) for k, v in gt.items()},
@@ -162,7 +166,13 @@ def test_cuda_decode_with_resize_factor(cuda_dev):
     ref = fo.decode_features(feats, w1.detach().cpu(), b1.detach().cpu(),
                              {k: (w.detach().cpu(), b.detach().cpu()) for k, (w, b) in br.items()}, dims, "clip",
                              resize_factor=8.0)
-    out = fd.decode_features(feats.to(cuda_dev), dec, dims, "clip", resize_factor=8.0)
+    with torch.no_grad():
+        out = fd.decode_features(feats.to(cuda_dev), dec, dims, "clip", resize_factor=8.0)
+        mlp = dec(feats.to(cuda_dev).permute(2, 0, 1)[None].contiguous())      # TwoLayerMLP.forward on a [1,F,H,W] map
+    ref_mlp = fo.mlp_forward(feats.permute(2, 0, 1)[None], w1.detach().cpu(), b1.detach().cpu(),
+                             {k: (w.detach().cpu(), b.detach().cpu()) for k, (w, b) in br.items()})
+    for k in dims:
+        torch.testing.assert_close(mlp[k].cpu(), ref_mlp[k], atol=1e-5, rtol=1e-4)
     assert out["clip"].shape == (48, 48, 72) and out["dino"].shape == (24, 11, 13)
     for k in dims:
         torch.testing.assert_close(out[k].cpu(), ref[k], atol=1e-5, rtol=1e-4)
@@ -173,12 +183,14 @@ def test_feature_decode_errors_are_loud(cuda_dev):
     from radegs_b200 import feature_decode as fd
     dims = {"clip": (8, 4, 4)}
     dec = _decoder(cuda_dev, 13, 16, dims)
-    with pytest.raises(RuntimeError, match="no CPU path"):
-        fd.decode_features(torch.zeros(8, 8, 13), dec, dims, "clip")
-    with pytest.raises(ValueError):
-        fd.decode_features(torch.zeros(8, 8, 12, device=cuda_dev), dec, dims, "clip")
+    with torch.no_grad():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fd.decode_features(torch.zeros(8, 8, 13), dec, dims, "clip")
+        with pytest.raises(ValueError):
+            fd.decode_features(torch.zeros(8, 8, 12, device=cuda_dev), dec, dims, "clip")
     with pytest.raises(ValueError):
         fd.features_loss(torch.zeros(8, 8, 13, device=cuda_dev), dec, dims, "clip",
                          {"clip": torch.zeros(8, 5, 4, device=cuda_dev)})
-    with pytest.raises(NotImplementedError):
-        fd.decode_features(torch.zeros(8, 8, 200, device=cuda_dev), _decoder(cuda_dev, 200, 16, dims), dims, "clip")
+    with torch.no_grad():
+        with pytest.raises(NotImplementedError):
+            fd.decode_features(torch.zeros(8, 8, 200, device=cuda_dev), _decoder(cuda_dev, 200, 16, dims), dims, "clip")
