@@ -294,7 +294,9 @@ sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ mean
     s_campos[t] = __ldcg(reinterpret_cast<const float4*>(src.base[g]) + k);
   }
   float* o = s_rows + t * RS;
-  for (int i = 0; i < row; ++i) o[i] = 0.f;
+  float acc[48];   // the sums live in registers (shared memory only stages the coalesced row store)
+#pragma unroll
+  for (int i = 0; i < 48; ++i) acc[i] = 0.f;
   __syncthreads();
   const int n = n0 + t;
   if (t < count) {
@@ -315,10 +317,17 @@ sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ mean
         rs::sh_basis(degree, x * inv, y * inv, z * inv, basis);
 #pragma unroll
         for (int q = 0; q < 16; ++q)
-          if (q < nb) { o[q * 3] += basis[q] * v[i].x; o[q * 3 + 1] += basis[q] * v[i].y; o[q * 3 + 2] += basis[q] * v[i].z; }
+          if (q < nb) {
+            acc[q * 3] = fmaf(basis[q], v[i].x, acc[q * 3]);
+            acc[q * 3 + 1] = fmaf(basis[q], v[i].y, acc[q * 3 + 1]);
+            acc[q * 3 + 2] = fmaf(basis[q], v[i].z, acc[q * 3 + 2]);
+          }
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 48; ++i)
+    if (i < row) o[i] = acc[i];      // coefficients beyond the active degree stay zero
   __syncthreads();
   smem_to_rows(s_rows, v_coeffs + (size_t)n0 * row, count, row, RS, t);
 }
