@@ -702,14 +702,12 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
           hit = footprint_hit(s, buf, j, a.exact_cull != 0, rcx, rcy, 3.5f, 3.5f);
         }
         unsigned m = __ballot_sync(RS_FULL_MASK, hit);
-        while (m) {
-          const int jj = g0 + __ffs(m) - 1;
-          m &= m - 1;
+        // survivors are taken two at a time: their alpha evaluations are independent (only the transmittance chain
+        // is sequential), which gives the scheduler two dependency chains to interleave
+        auto alpha_of = [&](int jj, float& dx, float (&dy)[2], float (&alpha)[2], bool (&ok)[2]) {
           const float4 q0 = s.q0[buf][jj], q1 = s.q1[buf][jj];
-          const float dx = q0.x - px;
+          dx = q0.x - px;
           const float A = __fmul_rn(__fmul_rn(q1.x, dx), dx), B = __fmul_rn(q1.y, dx);   // shared by both pixels of the column
-          float dy[2], alpha[2];
-          bool ok[2];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             dy[h] = q0.y - py[h];
@@ -717,6 +715,8 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
             alpha[h] = fminf(RS_ALPHA_MAX, q1.w * rs::fast_exp2(-sig));
             ok[h] = sig >= 0.f && alpha[h] >= RS_ALPHA_MIN;
           }
+        };
+        auto blend = [&](int jj, float dx, const float (&dy)[2], const float (&alpha)[2], const bool (&ok)[2]) {
           if constexpr (STATS) {
             ++st_evals;
             st_blend += __any_sync(RS_FULL_MASK, (ok[0] && T[0] * (1.f - alpha[0]) > RS_T_STOP) ||
@@ -755,6 +755,19 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
               }
             }
           }
+        };
+        while (m) {
+          const int ja = g0 + __ffs(m) - 1;
+          m &= m - 1;
+          const bool two = m != 0;
+          const int jb = two ? g0 + __ffs(m) - 1 : ja;
+          m &= m - 1;                                  // (0 & anything stays 0)
+          float dxa, dxb, dya[2], dyb[2], ala[2], alb[2];
+          bool oka[2], okb[2];
+          alpha_of(ja, dxa, dya, ala, oka);
+          alpha_of(jb, dxb, dyb, alb, okb);
+          blend(ja, dxa, dya, ala, oka);
+          if (two) blend(jb, dxb, dyb, alb, okb);
         }
         if (!__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f)) { warp_done = true; break; }
       }
