@@ -85,3 +85,26 @@ def test_python_layer_has_no_cpu_path():
         rasterization(means, quats, scales, torch.ones(N), torch.ones(N, 3), vm, Ks, 32, 32)   # packed=True default
     with pytest.raises(NotImplementedError):
         fully_fused_projection(means, torch.ones(N, 3, 3), None, None, vm, Ks, 32, 32)
+
+
+def test_header_is_plain_c_and_cxx():
+    """include/rade_b200.h is the drop-in boundary: it must compile as C99 and as C++ with no torch / CUDA headers."""
+    import shutil
+    import subprocess
+    hdr = ROOT / "include" / "rade_b200.h"
+    for cc, args in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++17", "-x", "c++"])):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not installed")
+        r = subprocess.run([cc, *args, "-Wall", "-Werror", "-fsyntax-only", str(hdr)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = hdr.read_text()
+    assert "torch" not in text.lower().replace("pytorch", "") or "#include <torch" not in text
+    assert "#include <cuda" not in text and "at::" not in text
+
+
+def test_every_entry_point_cites_the_reference():
+    """Each block of the header names the reference interface it replaces (file:line) or the SURVEY row."""
+    text = (ROOT / "include" / "rade_b200.h").read_text()
+    assert text.count(".py:") >= 8, "reference file:line citations are missing from the header"
+    for needle in ("rade_gs_model.py", "rade_features_model.py", "camera_utils.py", "mesh.py", "features.py"):
+        assert needle in text, needle
