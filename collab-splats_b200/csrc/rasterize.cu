@@ -945,13 +945,14 @@ __global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const
   // is broadcast by one shuffle, v_c[p][.] is read from shared memory (conflict free) and the totals land one channel
   // per lane, i.e. as coalesced REDs -- instead of 31 shuffle exchanges per 32 channels with lanes = pixels.
   constexpr bool CHLANE = DP >= 32;
-  static_assert(!CMMA || CHLANE, "the tensor-core colour reduction is for wide rows");
+  constexpr bool STAGED = CHLANE || CMMA;   // the tile's v_c rows are also kept in shared memory
+  static_assert(!CMMA || DP >= 16, "the tensor-core colour reduction needs at least one 16-channel tile");
   float* s_vc = reinterpret_cast<float*>(smem_raw + sizeof(Smem<DP, BATCH>));   // [RT][DP], CHLANE only
   // CMMA: per-warp parking lot of the tensor-core colour reduction (flush_color_mma)
   float* cm_vis = s_vc + RT * DP + warp * (CM_PEND * CM_VSTRIDE);               // [CM_PEND][CM_VSTRIDE]
   int* cm_row = reinterpret_cast<int*>(s_vc + RT * DP + (RT / 32) * (CM_PEND * CM_VSTRIDE)) + warp * CM_PEND;
   int cm_n = 0;
-  if constexpr (CHLANE) {
+  if constexpr (STAGED) {
 #pragma unroll
     for (int k = 0; k < DP; ++k) s_vc[t * DP + k] = v_c[k];   // (after the ED rescale above; made visible by the barrier below)
   }
@@ -1413,7 +1414,7 @@ template <int DP> struct BwdBatch { static constexpr int value = DP >= 64 ? 32 :
 
 template <int DP, bool ABSGRAD, bool CMMA> int launch_bwd3(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = BwdBatch<DP>::value;
-  const size_t smem = sizeof(Smem<DP, B>) + (DP >= 32 ? sizeof(float) * RT * DP : 0) +
+  const size_t smem = sizeof(Smem<DP, B>) + ((DP >= 32 || CMMA) ? sizeof(float) * RT * DP : 0) +
                       (CMMA ? (RT / 32) * (sizeof(float) * CM_PEND * CM_VSTRIDE + sizeof(int) * CM_PEND) : 0);
   cudaError_t e = cudaFuncSetAttribute(rasterize_bwd_kernel<DP, B, ABSGRAD, CMMA>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1422,7 +1423,7 @@ template <int DP, bool ABSGRAD, bool CMMA> int launch_bwd3(const RasterArgs& a, 
   RS_RETURN_LAST_ERROR();
 }
 template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
-  if constexpr (DP >= 32) {
+  if constexpr (DP >= 20) {   // measured: -3 % at 20 channels, -24..-29 % at 32-36, +5 % (worse) at 16
     if (g_color_mma) return launch_bwd3<DP, ABSGRAD, true>(a, st);
   }
   return launch_bwd3<DP, ABSGRAD, false>(a, st);
