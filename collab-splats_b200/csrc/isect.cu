@@ -226,6 +226,82 @@ isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __rest
   }
 }
 
+// Compact variant of the presorted path: the pair that goes through the radix passes is (camera|tile as u32, flatten id)
+// -- 8 bytes instead of 12 -- because the depth bits play no part in the remaining sort; the 64-bit keys the API
+// exposes are rebuilt after the sort by isect_finish32_kernel.
+__global__ void __launch_bounds__(IB)
+isect_emit_ordered32_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii,
+                            const int32_t* __restrict__ order, const long long* __restrict__ cum, int C, int N,
+                            int tile_w, int tile_h, int tile_bits, unsigned int* __restrict__ keys32,
+                            int32_t* __restrict__ flatten_ids) {
+  constexpr int WARPS = IB / 32;
+  __shared__ int s_pref[WARPS][33];
+  __shared__ int s_xmin[WARPS][32], s_ymin[WARPS][32], s_w[WARPS][32], s_e[WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long p = (long long)blockIdx.x * IB + threadIdx.x;
+  const long long total = (long long)C * N;
+  int cnt = 0, xmin = 0, ymin = 0, xmax = 0, ymax = 0, e = 0;
+  long long cum_p = 0;
+  if (p < total) {
+    e = __ldg(order + p);
+    cum_p = __ldg(cum + p);
+    if (tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax))
+      cnt = max((xmax - xmin) * (ymax - ymin), 0);
+  }
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(RS_FULL_MASK, incl, d);
+    if (lane >= d) incl += o;
+  }
+  const int warp_total = __shfl_sync(RS_FULL_MASK, incl, 31);
+  if (warp_total == 0) return;
+  const long long base = __shfl_sync(RS_FULL_MASK, cum_p - incl, 0);
+  s_pref[warp][lane + 1] = incl;
+  if (lane == 0) s_pref[warp][0] = 0;
+  s_xmin[warp][lane] = xmin; s_ymin[warp][lane] = ymin; s_w[warp][lane] = xmax - xmin; s_e[warp][lane] = e;
+  __syncwarp();
+  for (int k = lane; k < warp_total; k += 32) {
+    int lo = 0, hi = 32;   // owner j: pref[j] <= k < pref[j+1]
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (s_pref[warp][mid] <= k) lo = mid; else hi = mid;
+    }
+    const int r = k - s_pref[warp][lo];
+    const int w = s_w[warp][lo];
+    const int ry = r / w, rx = r - ry * w;
+    const int ee = s_e[warp][lo];
+    const unsigned int tile = (unsigned int)((s_ymin[warp][lo] + ry) * tile_w + s_xmin[warp][lo] + rx);
+    keys32[base + k] = ((unsigned int)(ee / N) << tile_bits) | tile;
+    flatten_ids[base + k] = ee;
+  }
+}
+
+// sorted (camera|tile, flatten id) pairs -> the API's 64-bit keys (camera|tile << 32 | depth bits) and the tile offsets
+__global__ void __launch_bounds__(IB)
+isect_finish32_kernel(const unsigned int* __restrict__ keys32, const int32_t* __restrict__ flatten_ids,
+                      const float* __restrict__ depths, long long M, int n_tiles, int tile_bits, int total,
+                      long long* __restrict__ isect_ids, int32_t* __restrict__ offsets) {
+  const long long i = (long long)blockIdx.x * IB + threadIdx.x;
+  if (i >= M) return;
+  const unsigned int tmask = (1u << tile_bits) - 1u;
+  const unsigned int k = __ldg(keys32 + i);
+  const unsigned int dbits = __float_as_uint(__ldg(depths + __ldg(flatten_ids + i)));
+  isect_ids[i] = (long long)(((unsigned long long)k << 32) | (unsigned long long)dbits);
+  const long long cur = (long long)(k >> tile_bits) * n_tiles + (long long)(k & tmask);
+  if (i == 0) {
+    for (long long t = 0; t <= cur; ++t) offsets[t] = 0;
+  } else {
+    const unsigned int kp = __ldg(keys32 + i - 1);
+    const long long prev = (long long)(kp >> tile_bits) * n_tiles + (long long)(kp & tmask);
+    for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+  }
+  if (i == M - 1) {
+    for (long long t = cur + 1; t < total; ++t) offsets[t] = (int32_t)M;
+  }
+}
+
 __global__ void __launch_bounds__(IB)
 offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, int n_tiles, int tile_bits, int total,
                      int32_t* __restrict__ offsets) {
@@ -351,5 +427,42 @@ extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, 
   if (!isect_ids) return RS_ERR_BAD_ARG;
   offset_encode_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, (int)n_tiles,
                                                                         tile_bits_for(n_tiles), (int)total, offsets);
+  RS_RETURN_LAST_ERROR();
+}
+
+// Compact presorted path (see isect_emit_ordered32_kernel): emits (camera|tile u32, flatten id) pairs in depth order.
+extern "C" int rs_isect_emit_ordered32(const float* means2d, const int32_t* radii, const int32_t* order,
+                                       const long long* cum_tiles, int C, int N, int tile_w, int tile_h,
+                                       uint32_t* keys32, int32_t* flatten_ids, void* stream) {
+  RsSpan span__("rs_isect_emit_ordered32", stream);
+  if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0) return RS_ERR_BAD_ARG;
+  if ((long long)C * N >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  if (C == 0 || N == 0) return RS_OK;
+  if (!means2d || !radii || !order || !cum_tiles || !keys32 || !flatten_ids) return RS_ERR_BAD_ARG;
+  const int tile_bits = tile_bits_for((long long)tile_w * tile_h);
+  int cam_bits = 0;
+  while ((1 << cam_bits) <= C) ++cam_bits;                 // floor(log2 C) + 1
+  if (tile_bits + cam_bits > 32) return RS_ERR_UNSUPPORTED;  // the caller falls back to the 64-bit path
+  isect_emit_ordered32_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, (const int2*)radii, order, cum_tiles, C, N, tile_w, tile_h, tile_bits, keys32,
+      flatten_ids);
+  RS_RETURN_LAST_ERROR();
+}
+
+// After the pairs are sorted on the key bits: isect_ids[M] (64-bit keys) and offsets[C*tile_h*tile_w] in one pass.
+extern "C" int rs_isect_finish32(const uint32_t* keys32, const int32_t* flatten_ids, const float* depths, long long M,
+                                 int C, int tile_w, int tile_h, long long* isect_ids, int32_t* offsets, void* stream) {
+  RsSpan span__("rs_isect_finish32", stream);
+  if (M < 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets) return RS_ERR_BAD_ARG;
+  if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  const long long n_tiles = (long long)tile_w * tile_h, total = n_tiles * C;
+  if (M == 0) {
+    cudaError_t e = cudaMemsetAsync(offsets, 0, sizeof(int32_t) * (size_t)total, (cudaStream_t)stream);
+    if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+    return RS_OK;
+  }
+  if (!keys32 || !flatten_ids || !depths || !isect_ids) return RS_ERR_BAD_ARG;
+  isect_finish32_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(
+      keys32, flatten_ids, depths, M, (int)n_tiles, tile_bits_for(n_tiles), (int)total, isect_ids, offsets);
   RS_RETURN_LAST_ERROR();
 }

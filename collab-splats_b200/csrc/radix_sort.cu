@@ -279,3 +279,11 @@ extern "C" int rs_argsort_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_
   return sort_pairs_impl<u32>((u32*)keys_a, (u32*)vals_a, (u32*)keys_b, (u32*)vals_b, true, M, begin_bit, end_bit,
                               temp, temp_bytes, stream);
 }
+
+// (uint32 key, int32 value) pairs, values read from vals_a (the compact intersection pairs, see isect.cu).
+extern "C" int rs_sort_pairs_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32_t* vals_b, long long M,
+                                 int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream) {
+  RsSpan span__("rs_sort_pairs_u32", stream);
+  return sort_pairs_impl<u32>((u32*)keys_a, (u32*)vals_a, (u32*)keys_b, (u32*)vals_b, false, M, begin_bit, end_bit,
+                              temp, temp_bytes, stream);
+}

@@ -28,6 +28,9 @@ TILE_SIZE = 16
 ISECT_SORT_METHOD = "presort"
 # Which pipeline rasterization() uses for isect_tiles + isect_offset_encode (identical outputs; tests compare them):
 #   "radix": isect_tiles (ISECT_SORT_METHOD) + isect_offset_encode -- the fastest measured on B200, the default
+#   "compact": depth argsort, (camera|tile u32, flatten id) pairs through two radix passes, 64-bit keys and offsets
+#            rebuilt together after the sort (8-byte instead of 12-byte pairs): the radix passes gain 7 % (they are
+#            latency-bound), the rebuild costs more than offset_encode alone -> 0.389 vs 0.378 ms, not the default
 #   "chunk": per-camera depth argsort + chunked counting sort (csrc/chunksort.cu), no radix passes over the pairs
 #            (measured slower: scattered 12-byte stores, profiles/r01_chunk_ab.txt);  "tile": csrc/tilesort.cu
 ISECT_PIPELINE = "radix"
@@ -282,6 +285,60 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     return (tiles, ids_b, flat_b) if where == 0 else (tiles, ids_a, flat_a)
 
 
+def _isect_compact(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int, key_bits: int):
+    """Presorted path with compact pairs: count -> stable depth argsort -> scan in depth order -> emit (camera|tile u32,
+    flatten id) -> radix sort on the key bits -> 64-bit keys + tile offsets in one pass."""
+    lib = _be.load()
+    C, N = depths.shape
+    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
+    _need_cuda(means2d, radii, depths)
+    dev = means2d.device
+    means2d, depths = _c(means2d), _c(depths)
+    radii = _c(radii, torch.int32)
+    n_elems = C * N
+    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
+    cum = torch.empty(n_elems, device=dev, dtype=torch.int64)
+    offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        st = _be.stream_ptr(dev)
+        _be.check(lib.rs_isect_count(_be.ptr(means2d), _be.ptr(radii), n_elems, tile_width, tile_height,
+                                     _be.ptr(tiles), st), "rs_isect_count")
+        dkeys = depths.clone().view(torch.int32)          # the sort clobbers its key buffers
+        dkeys_b = torch.empty_like(dkeys)
+        ord_a = torch.empty(n_elems, device=dev, dtype=torch.int32)
+        ord_b = torch.empty_like(ord_a)
+        sb = lib.rs_sort_pairs_temp_bytes(n_elems, 0, 32)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        where = _be.check(lib.rs_argsort_u32(_be.ptr(dkeys), _be.ptr(ord_a), _be.ptr(dkeys_b), _be.ptr(ord_b),
+                                             n_elems, 0, 32, _be.ptr(stemp), sb, st), "rs_argsort_u32")
+        order = ord_b if where == 0 else ord_a
+        tb = lib.rs_cumsum_temp_bytes(n_elems)
+        temp = torch.empty(tb, device=dev, dtype=torch.uint8)
+        _be.check(lib.rs_cumsum_gather_i32_i64(_be.ptr(tiles), _be.ptr(order), _be.ptr(cum), n_elems,
+                                               _be.ptr(temp), tb, st), "rs_cumsum_gather_i32_i64")
+        M = int(cum[n_elems - 1].item())
+        ids = torch.empty(M, device=dev, dtype=torch.int64)
+        if M == 0:
+            flat = torch.empty(0, device=dev, dtype=torch.int32)
+            _be.check(lib.rs_isect_finish32(None, None, None, 0, C, tile_width, tile_height, None, _be.ptr(offsets),
+                                            st), "rs_isect_finish32")
+            return tiles, ids, flat, offsets
+        k_a = torch.empty(M, device=dev, dtype=torch.int32)
+        f_a = torch.empty(M, device=dev, dtype=torch.int32)
+        k_b, f_b = torch.empty_like(k_a), torch.empty_like(f_a)
+        _be.check(lib.rs_isect_emit_ordered32(_be.ptr(means2d), _be.ptr(radii), _be.ptr(order), _be.ptr(cum), C, N,
+                                              tile_width, tile_height, _be.ptr(k_a), _be.ptr(f_a), st),
+                  "rs_isect_emit_ordered32")
+        sb = lib.rs_sort_pairs_temp_bytes(M, 0, key_bits)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        where = _be.check(lib.rs_sort_pairs_u32(_be.ptr(k_a), _be.ptr(f_a), _be.ptr(k_b), _be.ptr(f_b), M, 0, key_bits,
+                                                _be.ptr(stemp), sb, st), "rs_sort_pairs_u32")
+        keys, flat = (k_b, f_b) if where == 0 else (k_a, f_a)
+        _be.check(lib.rs_isect_finish32(_be.ptr(keys), _be.ptr(flat), _be.ptr(depths), M, C, tile_width, tile_height,
+                                        _be.ptr(ids), _be.ptr(offsets), st), "rs_isect_finish32")
+    return tiles, ids, flat, offsets
+
+
 def _isect_chunked(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int):
     """csrc/chunksort.cu: tiles_per_gauss, sorted isect_ids / flatten_ids and isect_offsets without sorting the pairs."""
     lib = _be.load()
@@ -339,7 +396,8 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
     """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go.
     -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32.
 
-    ``method=None``: the module default ``ISECT_PIPELINE`` ("radix").  ``method="radix"``: emit + onesweep radix
+    ``method=None``: the module default ``ISECT_PIPELINE`` ("radix").  ``method="compact"``: the presorted path with
+    32-bit camera|tile keys through the radix passes (falls back to "radix" when camera|tile needs more than 32 bits).  ``method="radix"``: emit + onesweep radix
     sort + offset encode.  ``method="chunk"``: per-camera depth argsort + chunked counting sort (csrc/chunksort.cu).  ``method="tile"``: the
     tile-partitioned path of csrc/tilesort.cu (per-tile histogram -> offsets, atomic-slot emission into tile
     segments, per-tile shared-memory bitonic sort; falls back to radix when a tile holds more than
@@ -350,6 +408,13 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
         raise NotImplementedError("tile_size must be 16")
     if method is None:
         method = ISECT_PIPELINE
+    if method == "compact":
+        C_ = depths.shape[0]
+        bits = _be.load().rs_tile_bits(tile_width, tile_height) + int(math.floor(math.log2(C_))) + 1
+        if bits > 32 or depths.numel() == 0:
+            method = "radix"
+        else:
+            return _isect_compact(means2d, radii, depths, tile_width, tile_height, bits)
     if method == "chunk":
         if tile_width * tile_height > _be.load().rs_isect_chunk_max_tiles() or depths.numel() == 0:
             method = "radix"

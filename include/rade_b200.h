@@ -238,6 +238,18 @@ int rs_project_lookup(const float* means2d /* [N,2] */, const int32_t* radii /* 
 int rs_scale_unless_one(float* const* bufs, const long long* counts, int n_bufs, const float* scale, void* stream);
 int rs_zero_bytes(void* ptr, long long bytes, void* stream);
 
+/* ---- compact presorted intersection path (opt-in; measured on par with the 64-bit path): the pairs that go through the radix
+ * passes are (camera|tile as u32, flatten id) -- the depth order is already established by the argsort -- and the
+ * 64-bit keys + tile offsets are produced together after the sort.  RS_ERR_UNSUPPORTED when camera|tile needs more
+ * than 32 bits. */
+int rs_isect_emit_ordered32(const float* means2d, const int32_t* radii, const int32_t* order,
+                            const long long* cum_tiles, int C, int N, int tile_w, int tile_h, uint32_t* keys32,
+                            int32_t* flatten_ids, void* stream);
+int rs_sort_pairs_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32_t* vals_b, long long M, int begin_bit,
+                      int end_bit, void* temp, long long temp_bytes, void* stream);
+int rs_isect_finish32(const uint32_t* keys32, const int32_t* flatten_ids, const float* depths, long long M, int C,
+                      int tile_w, int tile_h, long long* isect_ids, int32_t* offsets, void* stream);
+
 /* ---- chunked counting sort of the intersections (csrc/chunksort.cu): a sort-free path to the same isect_ids /
  * flatten_ids / isect_offsets as isect_tiles(sort=True) + isect_offset_encode.  `order` [C][N] i32: for each camera
  * the Gaussian indices in depth order (stable rs_argsort_u32 of that camera's depth bits).  G = entries per chunk

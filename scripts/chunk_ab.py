@@ -18,7 +18,7 @@ for cfg_id, views in ((2, 1), (5, 1), (4, 1), (4, 4)):
     radii, m2, depths = wr.fully_fused_projection(means, None, quats, scales, vm.to(dev), Ks.to(dev), W, H)[:3]
     tw, th = math.ceil(W / 16), math.ceil(H / 16)
     ref = None
-    for method in ("radix", "chunk", "radix", "chunk"):
+    for method in ("radix", "compact", "radix", "compact"):
         for _ in range(3): out = wr.isect_tiles_and_offsets(m2, radii, depths, 16, tw, th, method=method)
         lib.rs_timing_enable(1)
         torch.cuda.synchronize()

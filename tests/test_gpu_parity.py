@@ -807,6 +807,9 @@ def test_chunked_counting_sort_isect_matches_radix_path(cuda_dev, views, w, h, n
     assert i2.numel() == i1.numel() > 0
     assert torch.equal(t1, t2) and torch.equal(o1, o2)
     assert torch.equal(i1, i2) and torch.equal(f1, f2)
+    # the compact (32-bit camera|tile keys) pipeline (opt-in)
+    t3, i3, f3, o3 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th, method="compact")
+    assert torch.equal(t1, t3) and torch.equal(o1, o3) and torch.equal(i1, i3) and torch.equal(f1, f3)
     r_t, r_i, r_f = O.isect_tiles(means2d.cpu(), radii.cpu(), depths.cpu(), 16, tw, th)
     assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
     assert torch.equal(o2.cpu(), O.isect_offset_encode(r_i, views, tw, th))
@@ -819,8 +822,9 @@ def test_chunked_counting_sort_nothing_visible(cuda_dev):
     means2d = torch.rand(1, N, 2, device=cuda_dev) * 100
     radii = torch.zeros(1, N, 2, device=cuda_dev, dtype=torch.int32)
     depths = torch.rand(1, N, device=cuda_dev)
-    t, i, f, o = isect_tiles_and_offsets(means2d, radii, depths, 16, 7, 7, method="chunk")
-    assert i.numel() == 0 and f.numel() == 0 and int(t.sum()) == 0 and int(o.abs().sum()) == 0 and o.shape == (1, 7, 7)
+    for method in ("chunk", "compact"):
+        t, i, f, o = isect_tiles_and_offsets(means2d, radii, depths, 16, 7, 7, method=method)
+        assert i.numel() == 0 and f.numel() == 0 and int(t.sum()) == 0 and int(o.abs().sum()) == 0 and o.shape == (1, 7, 7)
 
 
 def test_forward_two_pixels_per_lane_variant(cuda_dev):
