@@ -242,7 +242,9 @@ class Workload:
         self.collectives_on = True
         if mode in ("push", "p2p", "allgather"):
             try:
-                self.exchange = ShGradExchange(self.cfg.n_gaussians, 1, self.device, mode=mode)
+                self.exchange = ShGradExchange(self.cfg.n_gaussians, 1, self.device, mode=mode,
+                                               push_engine=getattr(self, "push_engine", "dma"),
+                                               push_ctas=getattr(self, "push_ctas", 4))
             except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container)
                 print(f"ShGradExchange({mode}) unavailable: {e}; falling back to all-reduce", file=sys.stderr)
                 self.exchange_mode = "allreduce"
@@ -485,6 +487,9 @@ def main():
     ap.add_argument("--grad-exchange", default="push", choices=["push", "p2p", "allgather", "allreduce"],
                     help="N > 1: how the SH-coefficient gradients are combined (default: copy-engine push into peer "
                          "inboxes + local gather kernel; p2p = gather kernel pulls over NVLink)")
+    ap.add_argument("--push-engine", default="dma", choices=["dma", "sm"],
+                    help="push exchange: copy engines (cudaMemcpyAsync per peer) or one SM store kernel (rs_peer_push)")
+    ap.add_argument("--push-ctas", type=int, default=4, help="CTAs per peer of the SM store kernel")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE resident step between cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
@@ -522,6 +527,7 @@ def main():
     wl = Workload(args.config, device, rank, world)
     wl.fused_loss = not args.torch_loss
     if world > 1:
+        wl.push_engine, wl.push_ctas = args.push_engine, args.push_ctas
         wl.enable_grad_exchange(args.grad_exchange)
 
     def resident():
@@ -582,7 +588,7 @@ def main():
         multi = {"compute_only_ms_per_rank": [round(float(v[0]), 4) for v in everyone],
                  "n_isects_per_rank": [int(v[1]) for v in everyone],
                  "exchange_spans_ms_rank0": {k: round(spans[k][0] / 5, 4) for k in keys if k in spans},
-                 "grad_exchange": wl.exchange_mode,
+                 "grad_exchange": wl.exchange_mode + ("/" + args.push_engine if wl.exchange_mode == "push" else ""),
                  "note": "step time = slowest rank's compute + exposed exchange; rs_peer_wait is time spent waiting "
                          "for the slowest peer's colour gradients"}
 

@@ -32,6 +32,24 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int n_ranks, u
   *timed_out = 1;
 }
 
+struct PushDsts {
+  uint4* dst[16];
+};
+
+// SM-driven push: every destination gets gridDim.x CTAs that stream `src` into it with 16-byte stores (posted writes
+// over NVLink), four loads in flight per thread
+__global__ void __launch_bounds__(256) peer_push_kernel(PushDsts d, const uint4* __restrict__ src, long long n16) {
+  uint4* __restrict__ dst = d.dst[blockIdx.y];
+  const long long stride = (long long)gridDim.x * 256;
+  long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    const uint4 a = __ldg(src + i), b = __ldg(src + i + stride), c = __ldg(src + i + 2 * stride),
+                e = __ldg(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = e;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldg(src + i);
+}
+
 }  // namespace
 
 extern "C" int rs_peer_alloc(long long bytes, void** ptr) {
@@ -106,5 +124,23 @@ extern "C" int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long 
   const long long cycles = (long long)timeout_ms * 1900000ll;   // ~1.9 GHz SM clock
   peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)local_flags, n_ranks, value, cycles,
                                                        timed_out_dev);
+  RS_RETURN_LAST_ERROR();
+}
+
+// The same transfer as n_dst rs_peer_copy calls, driven by the SMs instead of the copy engines: one kernel,
+// ctas_per_dst CTAs per destination (dsts: HOST array of n_dst <= 16 peer-mapped device pointers; bytes % 16 == 0).
+// On an NVSwitch box the copy engines deliver ~380 GB/s for 7 x 16 MB, SM stores more.
+extern "C" int rs_peer_push(void* const* dsts, int n_dst, const void* src, long long bytes, int ctas_per_dst,
+                            void* stream) {
+  RsSpan span__("rs_peer_push", stream);
+  if (n_dst < 0 || n_dst > 16 || bytes < 0 || (bytes & 15) || ctas_per_dst <= 0) return RS_ERR_BAD_ARG;
+  if (n_dst == 0 || bytes == 0) return RS_OK;
+  if (!dsts || !src) return RS_ERR_BAD_ARG;
+  PushDsts d;
+  for (int i = 0; i < n_dst; ++i) {
+    if (!dsts[i]) return RS_ERR_BAD_ARG;
+    d.dst[i] = (uint4*)dsts[i];
+  }
+  peer_push_kernel<<<dim3(ctas_per_dst, n_dst), 256, 0, (cudaStream_t)stream>>>(d, (const uint4*)src, bytes / 16);
   RS_RETURN_LAST_ERROR();
 }

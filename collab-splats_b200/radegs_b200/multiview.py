@@ -113,6 +113,7 @@ class ShGradExchange:
     """
 
     def __init__(self, n_gaussians: int, cams_per_rank: int, device, group=None, mode: str = "push",
+                 push_engine: str = "dma", push_ctas: int = 4,
                  timeout_ms: int = 5000):
         from radegs_b200 import backend as be
         import ctypes
@@ -133,6 +134,9 @@ class ShGradExchange:
         self._pending = None
         self._out = None
         self.mode = mode
+        if push_engine not in ("dma", "sm"):
+            raise ValueError("push_engine must be 'dma' (copy engines) or 'sm' (store kernel)")
+        self.push_engine, self.push_ctas = push_engine, int(push_ctas)
         self._peer_ptrs = []        # imported mappings, closed in close()
         self._own = []              # own cudaMalloc'ed blocks
         cams = [self.C] * self.world
@@ -253,15 +257,25 @@ class ShGradExchange:
             streams = self._copy_streams
             for s_ in streams:
                 s_.wait_event(fork)
-            for i, g in enumerate(peers):          # start with the next rank so the ranks do not all hit rank 0 first
-                g = peers[(i + self.rank) % len(peers)]
-                with torch.cuda.stream(streams[i % len(streams)]):
-                    be.check(lib.rs_peer_copy(ct.c_void_p(self.region_base[g] + self._slot(self.rank)), ct.c_void_p(src),
-                                              self.region_bytes, be.stream_ptr(self.device)), "rs_peer_copy")
-            for s_ in streams[1:]:
-                ev = torch.cuda.Event()
-                ev.record(s_)
-                streams[0].wait_event(ev)
+            if self.push_engine == "sm" and peers:
+                # one kernel, a few CTAs per peer, 16-byte posted stores over NVLink (rs_peer_push) on a side stream
+                order = [peers[(i + self.rank) % len(peers)] for i in range(len(peers))]
+                dsts = (ct.c_void_p * len(order))(*[self.region_base[g] + self._slot(self.rank) for g in order])
+                with torch.cuda.stream(streams[0]):
+                    be.check(lib.rs_peer_push(ct.cast(dsts, ct.c_void_p), len(order), ct.c_void_p(src),
+                                              self.region_bytes, self.push_ctas, be.stream_ptr(self.device)),
+                             "rs_peer_push")
+            else:
+                for i, g in enumerate(peers):      # start with the next rank so the ranks do not all hit rank 0 first
+                    g = peers[(i + self.rank) % len(peers)]
+                    with torch.cuda.stream(streams[i % len(streams)]):
+                        be.check(lib.rs_peer_copy(ct.c_void_p(self.region_base[g] + self._slot(self.rank)),
+                                                  ct.c_void_p(src), self.region_bytes, be.stream_ptr(self.device)),
+                                 "rs_peer_copy")
+                for s_ in streams[1:]:
+                    ev = torch.cuda.Event()
+                    ev.record(s_)
+                    streams[0].wait_event(ev)
             with torch.cuda.stream(streams[0]):    # the flag goes up only after every copy has landed
                 be.check(lib.rs_peer_signal(be.ptr(self.flag_ptrs_dev), self.world, self.rank, self.step,
                                             be.stream_ptr(self.device)), "rs_peer_signal")

@@ -215,7 +215,10 @@ int rs_peer_handle_bytes(void);
 int rs_peer_export(void* ptr, void* handle_out);
 int rs_peer_import(const void* handle, void** ptr);
 int rs_peer_unimport(void* ptr);
-int rs_peer_copy(void* dst, const void* src, long long bytes, void* stream); /* copy engines, peer pointers ok */
+int rs_peer_copy(void* dst, const void* src, long long bytes, void* stream);
+/* the same transfer to n_dst <= 16 peers (dsts: HOST array of peer-mapped device pointers; bytes % 16 == 0) driven by
+ * the SMs: one kernel, ctas_per_dst CTAs per destination, 16-byte posted stores over NVLink */
+int rs_peer_push(void* const* dsts, int n_dst, const void* src, long long bytes, int ctas_per_dst, void* stream); /* copy engines, peer pointers ok */
 int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsigned long long value, void* stream);
 int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long long value, int timeout_ms, int* timed_out_dev,
                  void* stream);

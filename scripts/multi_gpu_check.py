@@ -57,12 +57,13 @@ if rank == 0:
         for r, g in zip(ref, step([c], None, False)):
             r += g
 report = {}
-for mode in ("push", "p2p", "allgather"):
+for mode, engine in (("push", "dma"), ("push", "sm"), ("p2p", "dma"), ("allgather", "dma")):
     try:
-        ex = ShGradExchange(N, 1, dev, mode=mode)
+        ex = ShGradExchange(N, 1, dev, mode=mode, push_engine=engine)
     except Exception as e:  # noqa: BLE001
         report[mode] = f"setup failed: {e}"
         continue
+    mode = mode + ("/sm" if engine == "sm" else "")
     got = step([rank], ex, True)
     got2 = step([rank], ex, True)
     ex.check()
