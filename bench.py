@@ -362,10 +362,13 @@ def fp32_accounting(wl, lib, backend, st, device):
     """FP32 roofline of the compositing kernels: algorithmic flops 12*Q + (16+2D)*Qc forward and
     14*Q' + (60+6D)*Qc backward over the measured in-step durations, against a sustained FFMA probe run here."""
     counters = torch.zeros(4, device=device, dtype=torch.int64)
-    lib.rs_raster_set_stats(backend.ptr(counters))
-    with torch.no_grad():
-        wl.forward_loss(wl.viewmat, wl.K, wl.gt)          # instrumented forward, never timed
-    lib.rs_raster_set_stats(None)
+    from gsplat.cuda import _wrapper as W
+    W.RASTER_STATS = counters
+    try:
+        with torch.no_grad():
+            wl.forward_loss(wl.viewmat, wl.K, wl.gt)      # instrumented forward, never timed
+    finally:
+        W.RASTER_STATS = None
     Q, Qc, evals, blends = [int(v) for v in counters.tolist()]
     meta = wl.last_meta
     D = 4
@@ -390,7 +393,7 @@ def fp32_accounting(wl, lib, backend, st, device):
             "warp_evaluations_blending": blends, "fwd_algorithmic_tflops": round(f, 2),
             "bwd_algorithmic_tflops": round(b, 2), "fma_probe_tflops": round(peak, 2),
             "fwd_frac_of_probe": round(f / peak, 3), "bwd_frac_of_probe": round(b / peak, 3),
-            "warp_block": "8x8 pixels (two per lane)" if lib.rs_raster_get_variant() == 1 else "8x4 pixels",
+            "warp_block": "8x8 pixels (two per lane)",
             "note": "algorithmic flops count every pair the reference's per-pixel loop visits (SURVEY 8d); the "
                     "kernels skip most of them with the warp-level footprint test, so this is work-equivalent "
                     "throughput, not executed flops"}

@@ -169,7 +169,8 @@ struct RasterArgs {
   const float* Ks;           // [C][9]
   int C, N, W, H, tile_w, tile_h, D, color_per_cam;
   int ed_channel;            // >= 0: that colour channel is divided by max(alpha, 1e-10) ("ED" modes); -1: none
-  int exact_cull;            // footprint test the records were packed for (rs_pack_geom's cull mode)
+  int exact_cull;            // footprint test the records were packed for (!RS_RASTER_CULL_BBOX)
+  int flags;                 // RS_RASTER_* options of the call
   const int* offsets;        // [C*tile_h*tile_w]
   const int* flatten_ids;    // [M]
   int M;
@@ -1364,6 +1365,317 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd2_kernel(const RasterA
   rs::cp_async_wait_all();
 }
 
+// ------------------------------------------------------------------------------------------------ backward, 2 px/lane, MMA reduction
+// Same per-pixel arithmetic as rasterize_bwd2_kernel, but the per-Gaussian reduction over the warp's 64 pixels is a
+// tensor-core contraction instead of a shuffle tree.  Every one of the 16 sums of a (warp, Gaussian) pair is linear in
+// one of two per-pixel factors with PER-PIXEL CONSTANT coefficients:
+//   vis[p]     x { v_n(3), v_c(4), v_ds, v_ds*u, v_ds*v }            (10 columns; u, v = pixel offset from the warp
+//   v_sigma[p] x { 1, u, v, u^2, u v, v^2 }                          ( 6 columns   rectangle's centre: +-0.5 .. +-3.5)
+// so a lane only PARKS (vis, v_sigma) of its two pixels (one 16-byte shared store) and every B3_PEND Gaussians the warp
+// contracts the parked block with mma.sync m16n8k8 (TF32): A = the constants, transposed (rows = output columns,
+// k = 8 pixels per step, 8 steps), B = parked values (k = pixels, n = 8 Gaussians).  The parked values are split
+// x = hi + lo on the fly and the arbitrary constants once per tile (3 products per step; the monomials are exact in
+// TF32: 2 products), so the sums keep fp32-level accuracy (|error| <= 2^-20 of each term).  The raw moments about the
+// rectangle centre are shifted to the Gaussian's centre (dx = X - u) and committed with one 16-byte vector RED per
+// lane: 8 Gaussians x 64 bytes per instruction.  Replaces 16 SHFL + ~60 ALU/FMA issue slots per (warp, Gaussian) by
+// ~25.
+constexpr int B3_PEND = 8;       // Gaussians parked per warp before a contraction (= the MMA's N)
+constexpr int B3_PSTRIDE = 36;   // float4 row stride of the parking lot: fragment loads hit 8 distinct 16-byte bank groups
+constexpr int B3_MSTRIDE = 20;   // float row stride of the moment rows (conflict-free transposing stores)
+
+// A fragments (m16n8k8: a0 = (row gid, k tig), a1 = (row gid + 8, k tig), a2 = (row gid, k tig + 4), a3 = (row gid + 8,
+// k tig + 4)) are stored as ready-made register quads, one 16-byte load each.  The 10 "vis" columns sit in rows 0..4 and
+// 8..12, the 6 monomials in rows 0..2 and 8..10, so that only lanes with gid < 5 (gid < 3) hold anything and the others
+// keep a quad of zeros in registers for the whole contraction.
+// The monomial quads: entry [ks][lane < 12] = rows gid, gid + 3 of {1, u, v | u^2, u v, v^2} at pixel lane 4 ks + tig,
+// pixels h0 / h1 (u = (l & 7) - 3.5, v = (l >> 3) + 4 h - 3.5) -- the same for every warp of every tile.
+struct B3SigTab { float4 v[8 * 12]; };
+constexpr float b3_mono(int row, float u, float v) {
+  return row == 0 ? 1.f : row == 1 ? u : row == 2 ? v : row == 3 ? u * u : row == 4 ? u * v : v * v;
+}
+constexpr B3SigTab b3_make_sig() {
+  B3SigTab t{};
+  for (int ks = 0; ks < 8; ++ks)
+    for (int lane = 0; lane < 12; ++lane) {
+      const int row = lane >> 2, src = 4 * ks + (lane & 3);
+      const float u = (float)(src & 7) - 3.5f, v0 = (float)(src >> 3) - 3.5f, v1 = v0 + 4.f;
+      t.v[ks * 12 + lane] = float4{b3_mono(row, u, v0), b3_mono(row + 3, u, v0), b3_mono(row, u, v1), b3_mono(row + 3, u, v1)};
+    }
+  return t;
+}
+__device__ const B3SigTab g_b3_sig = b3_make_sig();
+
+struct Bwd3Warp {                          // per-warp shared memory
+  float4 park[B3_PEND * B3_PSTRIDE];       // [g][pixel lane] = (vis h0, vis h1, v_sigma h0, v_sigma h1)
+  float4 meta[B3_PEND];                    // (x_g - rcx, y_g - rcy, flatten id bits, -)
+  float mom[B3_PEND * B3_MSTRIDE];         // [g][column] raw moments, transposed out of the C fragments
+  float4 cah[8 * 20];                      // TF32 heads of the "vis" constants: [k step][lane < 20] = (a0, a1, a2, a3)
+  float4 cal[8 * 20];                      // their tails
+  float4 zero;                             // what the lanes without constant rows read
+};
+struct Bwd3Cta {                           // per-CTA shared memory
+  float4 sig[8 * 12];                      // copy of g_b3_sig
+};
+
+__device__ __forceinline__ void b3_split(float x, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;        // TF32 head by truncation (exactly representable)
+  lo = __float_as_uint(x - __uint_as_float(hi)); // exact remainder; the tensor core reads its leading 11 bits
+}
+
+__device__ __forceinline__ void bwd3_flush(Bwd3Warp& w, const float4* __restrict__ sig_tab, int n,
+                                           float* __restrict__ geom_grad, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  __syncwarp();   // the parked rows are complete
+  float cv[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4* prow = w.park + gid * B3_PSTRIDE + tig;
+  // lanes without rows (gid >= 5, gid >= 3) read a quad of zeros instead (stride 0): the loop body stays branch free
+  const float4* pch = lane < 20 ? w.cah + lane : &w.zero;
+  const float4* pcl = lane < 20 ? w.cal + lane : &w.zero;
+  const float4* pcg = lane < 12 ? sig_tab + lane : &w.zero;
+  const int sv = lane < 20 ? 20 : 0, sg = lane < 12 ? 12 : 0;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const float4 p = prow[4 * ks];   // Gaussian gid, pixel lane 4 ks + tig: k = tig is its pixel h0, k = tig + 4 its pixel h1
+    const float4 ch = pch[ks * sv], cl = pcl[ks * sv], cg = pcg[ks * sg];
+    unsigned vh0, vl0, vh1, vl1, sh0, sl0, sh1, sl1;
+    b3_split(p.x, vh0, vl0); b3_split(p.y, vh1, vl1);
+    b3_split(p.z, sh0, sl0); b3_split(p.w, sh1, sl1);
+    const unsigned ah[4] = {__float_as_uint(ch.x), __float_as_uint(ch.y), __float_as_uint(ch.z), __float_as_uint(ch.w)};
+    const unsigned al[4] = {__float_as_uint(cl.x), __float_as_uint(cl.y), __float_as_uint(cl.z), __float_as_uint(cl.w)};
+    const unsigned as[4] = {__float_as_uint(cg.x), __float_as_uint(cg.y), __float_as_uint(cg.z), __float_as_uint(cg.w)};
+    mma_tf32_16x8x8(cv, ah, vh0, vh1);
+    mma_tf32_16x8x8(cv, al, vh0, vh1);
+    mma_tf32_16x8x8(cv, ah, vl0, vl1);
+    mma_tf32_16x8x8(cs, as, sh0, sh1);
+    mma_tf32_16x8x8(cs, as, sl0, sl1);
+  }
+  // C fragments -> mom[g][column]: (c0, c1) = row gid, (c2, c3) = row gid + 8 of Gaussians 2 tig, 2 tig + 1
+  float* const m = w.mom;
+  if (gid < 5) {
+    m[(2 * tig) * B3_MSTRIDE + gid] = cv[0];
+    m[(2 * tig + 1) * B3_MSTRIDE + gid] = cv[1];
+    m[(2 * tig) * B3_MSTRIDE + 5 + gid] = cv[2];
+    m[(2 * tig + 1) * B3_MSTRIDE + 5 + gid] = cv[3];
+  }
+  if (gid < 3) {
+    m[(2 * tig) * B3_MSTRIDE + 10 + gid] = cs[0];
+    m[(2 * tig + 1) * B3_MSTRIDE + 10 + gid] = cs[1];
+    m[(2 * tig) * B3_MSTRIDE + 13 + gid] = cs[2];
+    m[(2 * tig + 1) * B3_MSTRIDE + 13 + gid] = cs[3];
+  }
+  __syncwarp();
+  // lane (g, q): quarter q of Gaussian g's 16-float gradient record.  Moments about the rectangle centre -> sums over
+  // dx = X - u, dy = Y - v:  S v dx = X M00 - M10,  S v dx^2 = X (S v dx) - (X M10 - M20),  S v dx dy = X (S v dy) - (Y M10 - M11) ...
+  const int g = gid, q = tig;
+  if (g < n) {
+    const float4* r = reinterpret_cast<const float4*>(m + g * B3_MSTRIDE);
+    const float4 m0 = r[0], m1 = r[1], m2 = r[2], m3 = r[3], mt = w.meta[g];
+    // m0 = (n0 n1 n2 c0)  m1 = (c1 c2 c3 Vt0)  m2 = (Vtu Vtv M00 M10)  m3 = (M01 M20 M11 M02)
+    const float X = mt.x, Y = mt.y;
+    float4 out;
+    if (q == 0) {
+      const float s10 = fmaf(X, m2.z, -m2.w), s01 = fmaf(Y, m2.z, -m3.x);
+      out.x = s10;
+      out.y = s01;
+      out.z = 0.5f * fmaf(X, s10, -fmaf(X, m2.w, -m3.y));
+      out.w = fmaf(X, s01, -fmaf(Y, m2.w, -m3.z));
+    } else if (q == 1) {
+      const float s01 = fmaf(Y, m2.z, -m3.x);
+      out.x = 0.5f * fmaf(Y, s01, -fmaf(Y, m3.x, -m3.w));
+      out.y = m2.z;
+      out.z = m1.w;
+      out.w = fmaf(X, m1.w, -m2.x);
+    } else if (q == 2) {
+      out = make_float4(fmaf(Y, m1.w, -m2.y), m0.x, m0.y, m0.z);
+    } else {
+      out = make_float4(m0.w, m1.x, m1.y, m1.z);
+    }
+    atomicAdd(reinterpret_cast<float4*>(geom_grad + (size_t)__float_as_int(mt.z) * 16 + 4 * q), out);
+  }
+}
+
+template <int BATCH, int MINB>
+__global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterArgs a) {
+  constexpr int DP = 4;
+  static_assert(BATCH <= RT2, "at most one id per thread");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  Bwd3Warp& w = reinterpret_cast<Bwd3Warp*>(smem_raw + sizeof(Smem<DP, BATCH>))[warp];
+  Bwd3Cta& wc = *reinterpret_cast<Bwd3Cta*>(smem_raw + sizeof(Smem<DP, BATCH>) + (RT2 / 32) * sizeof(Bwd3Warp));
+  const int tile_id = blockIdx.x;
+  const int tiles_per_cam = a.tile_w * a.tile_h;
+  const int cam = tile_id / tiles_per_cam;
+  const int tl = tile_id - cam * tiles_per_cam;
+  const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
+  const int start = __ldg(a.offsets + tile_id);
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
+  const int pxi = x0 + (lane & 7);
+  const float px = pxi + 0.5f;
+  const float rcx = x0 + 4.0f, rcy = y0 + 4.0f;
+
+  float py[2], v_c[2][4], v_ds[2], v_n[2][3], tfin[2], T[2], R[2];
+  int last_id[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int pyi = y0 + (lane >> 3) + 4 * h;
+    const bool inside = pxi < a.W && pyi < a.H;
+    const size_t pix = inside ? ((size_t)cam * a.H + pyi) * a.W + pxi : 0;
+    py[h] = pyi + 0.5f;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) v_c[h][k] = (inside && k < a.D) ? __ldg(a.v_colors + pix * a.D + k) : 0.f;
+    const float T_final = inside ? a.out_T[pix] : 1.f;
+    float v_alpha_ed = 0.f;
+    if (a.ed_channel >= 0 && inside) {   // select form: a dynamic index would push v_c into local memory
+      const float alpha_out = 1.f - T_final;
+      const float sc = 1.f / fmaxf(alpha_out, 1e-10f);
+      const float oc = __ldg(a.out_colors + pix * a.D + a.ed_channel);
+      const float vce = __ldg(a.v_colors + pix * a.D + a.ed_channel);
+      if (alpha_out > 1e-10f) v_alpha_ed = -oc * vce * sc;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) v_c[h][k] *= (k == a.ed_channel) ? sc : 1.f;
+    }
+    last_id[h] = inside ? a.last_ids[pix] : start - 1;   // an outside pixel owns no list entry: never "valid"
+    const float il = inside ? inv_ray_len(a, cam, px, py[h]) : 0.f;
+    v_ds[h] = inside ? __ldg(a.v_dexp + pix) * il : 0.f;
+    if (inside) commit_median_grad(a, a.median_ids[pix], __ldg(a.v_dmed + pix) * il, px, py[h]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v_n[h][k] = inside ? __ldg(a.v_normals + pix * 3 + k) : 0.f;
+    float bgdot = 0.f;
+    if (a.backgrounds) {
+#pragma unroll
+      for (int k = 0; k < DP; ++k)
+        if (k < a.D) bgdot += __ldg(a.backgrounds + (size_t)cam * a.D + k) * v_c[h][k];
+    }
+    tfin[h] = inside ? T_final * (__ldg(a.v_alphas + pix) + v_alpha_ed - bgdot) : 0.f;
+    T[h] = T_final;
+    R[h] = 0.f;
+  }
+
+  // ---- A fragments of the constants (once per tile).  k step ks covers pixel lanes 4 ks .. 4 ks + 3: k = j is pixel
+  // h0 of lane 4 ks + j, k = j + 4 its pixel h1.  Columns: 0..2 v_n, 3..6 v_c, 7 v_ds, 8 v_ds*u, 9 v_ds*v; lane
+  // (gid < 5, tig) holds columns gid (row gid) and 5 + gid (row gid + 8).  Heads by truncation, tails exact (the
+  // tensor core reads their leading 11 bits).
+  {
+    const int gid = lane >> 2, tig = lane & 3;
+    const float u_own = (float)(lane & 7) - 3.5f;
+    float4* sc = w.park;   // scratch [lane][5 float4]: 10 columns x 2 pixels
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float v_own = (float)((lane >> 3) + 4 * h) - 3.5f;
+      float* d = reinterpret_cast<float*>(sc + lane * 5) + h * 10;
+      d[0] = v_n[h][0]; d[1] = v_n[h][1]; d[2] = v_n[h][2];
+      d[3] = v_c[h][0]; d[4] = v_c[h][1]; d[5] = v_c[h][2]; d[6] = v_c[h][3];
+      d[7] = v_ds[h]; d[8] = v_ds[h] * u_own; d[9] = v_ds[h] * v_own;
+    }
+    if (t < 8 * 12) wc.sig[t] = g_b3_sig.v[t];   // (visible to the other warps after the barrier below)
+    if (lane == 0) w.zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    if (lane < 20) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const float* r = reinterpret_cast<const float*>(sc + (4 * ks + tig) * 5);
+        const float c[4] = {r[gid], r[5 + gid], r[10 + gid], r[15 + gid]};
+        float hi[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hi[i] = __uint_as_float(__float_as_uint(c[i]) & 0xffffe000u);
+        w.cah[ks * 20 + lane] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        w.cal[ks * 20 + lane] = make_float4(c[0] - hi[0], c[1] - hi[1], c[2] - hi[2], c[3] - hi[3]);
+      }
+    }
+    __syncwarp();   // the scratch rows (parking lot) may be overwritten from here on
+  }
+
+  int warp_last = max(last_id[0], last_id[1]);
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) warp_last = max(warp_last, __shfl_xor_sync(RS_FULL_MASK, warp_last, d));
+  if (lane == 0) s.red[warp] = warp_last;
+  __syncthreads();
+  int blk_last = start - 1;
+#pragma unroll
+  for (int wi = 0; wi < RT2 / 32; ++wi) blk_last = max(blk_last, s.red[wi]);
+  const int nb = blk_last >= start ? (blk_last - start) / BATCH + 1 : 0;
+
+  if (nb > 0) {
+    const int bl = nb - 1;
+    if (t < BATCH) { const int i = start + bl * BATCH + t; s.ids[bl & 1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+    __syncthreads();
+    issue_gather<DP, BATCH, RT2>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
+    if (bl >= 1 && t < BATCH) s.ids[(bl - 1) & 1][t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + t);
+  }
+  int np = 0;   // Gaussians parked
+  for (int b = nb - 1; b >= 0; --b) {
+    rs::cp_async_wait_all();
+    __syncthreads();
+    int next_id = 0;
+    if (b >= 1) {
+      issue_gather<DP, BATCH, RT2>(s, (b - 1) & 1, BATCH, a, t);
+      if (b >= 2 && t < BATCH) next_id = __ldg(a.flatten_ids + start + (b - 2) * BATCH + t);
+    }
+    const int buf = b & 1;
+    const int base_idx = start + b * BATCH;
+    const int hi = min(min(BATCH, end - base_idx) - 1, warp_last - base_idx);
+    for (int g0 = hi >= 0 ? (hi & ~31) : -32; g0 >= 0; g0 -= 32) {
+      const int j = g0 + lane;
+      bool hit = false;
+      if (j <= hi) hit = footprint_hit(s, buf, j, a.exact_cull != 0, rcx, rcy, 3.5f, 3.5f);
+      unsigned m = __ballot_sync(RS_FULL_MASK, hit);
+      while (m) {
+        const int bit = 31 - __clz(m);   // back to front
+        m &= ~(1u << bit);
+        const int jj = g0 + bit;
+        const int idx = base_idx + jj;
+        const float2 xy = *reinterpret_cast<const float2*>(&s.q0[buf][jj]);
+        const float4 q1 = s.q1[buf][jj];
+        const float dx = xy.x - px;
+        const float adx2 = __fmul_rn(__fmul_rn(q1.x, dx), dx), bdx = __fmul_rn(q1.y, dx);
+        float dy[2], am[2];
+        bool valid[2], unc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          dy[h] = xy.y - py[h];
+          const float sig = sigma_col(adx2, bdx, q1.z, dy[h]);
+          const float oe = q1.w * rs::fast_exp2(-sig);
+          const float alpha = fminf(RS_ALPHA_MAX, oe);
+          valid[h] = idx <= last_id[h] && sig >= 0.f && alpha >= RS_ALPHA_MIN;
+          am[h] = valid[h] ? alpha : 0.f;   // an invalid pair acts as alpha = 0: every term below is an exact 0
+          unc[h] = valid[h] && oe <= RS_ALPHA_MAX;
+        }
+        if (!__any_sync(RS_FULL_MASK, valid[0] || valid[1])) continue;
+        const float4 q2 = s.q2[buf][jj], q3 = s.q3[buf][jj];
+        const float4 cc = *reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+        const float tb = fmaf(q2.y, dx, q2.x);
+        float pv[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float ra = rs::fast_rcp(1.f - am[h]);
+          T[h] *= ra;   // transmittance in front of this Gaussian
+          const float vis = am[h] * T[h];
+          const float tt = fmaf(q2.z, dy[h], tb);
+          float wv = v_ds[h] * tt;
+          wv = fmaf(v_n[h][0], q3.x, wv); wv = fmaf(v_n[h][1], q3.y, wv); wv = fmaf(v_n[h][2], q3.z, wv);
+          wv = fmaf(v_c[h][0], cc.x, wv); wv = fmaf(v_c[h][1], cc.y, wv);
+          wv = fmaf(v_c[h][2], cc.z, wv); wv = fmaf(v_c[h][3], cc.w, wv);
+          const float v_alpha = fmaf(T[h], wv, ra * (tfin[h] - R[h]));
+          R[h] = fmaf(vis, wv, R[h]);
+          pv[h] = vis;
+          pv[2 + h] = unc[h] ? -am[h] * v_alpha : 0.f;   // v_sigma
+        }
+        w.park[np * B3_PSTRIDE + lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        if (lane == 0) w.meta[np] = make_float4(xy.x - rcx, xy.y - rcy, q2.w, 0.f);
+        if (++np == B3_PEND) {
+          bwd3_flush(w, wc.sig, B3_PEND, a.geom_grad, lane);
+          np = 0;
+        }
+      }
+    }
+    if (b >= 2 && t < BATCH) s.ids[b & 1][t] = next_id;
+  }
+  rs::cp_async_wait_all();
+  if (np > 0) bwd3_flush(w, wc.sig, np, a.geom_grad, lane);   // rows >= np hold stale values: their columns are never committed
+}
+
 // ------------------------------------------------------------------------------------------------ launch
 template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
@@ -1374,10 +1686,9 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   rasterize_fwd_kernel<DP, B, STATS><<<a.C * a.tile_w * a.tile_h, RT, smem, st>>>(a);
   RS_RETURN_LAST_ERROR();
 }
-static int g_bwd2_minb = 4;   // tuning knob (rs_raster_set_occupancy): register cap of the 2-px backward
-static int g_raster_variant = 1;  // DP == 4 only.  0: one pixel per lane (8x4 per warp); 1 (default): two pixels per lane (8x8 per warp)
-
-static int g_color_mma = 1;   // wide rows: 1 = tensor-core colour blend / colour-gradient reduction (3xTF32), 0 = SIMT
+// per-call options (include/rade_b200.h); the values must match the header's
+constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_SHUFFLE = 0x8;
+static inline int bwd_tune(int flags) { return (flags >> 8) & 0xf; }
 
 template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
   constexpr int B = Batch<DP>::value;
@@ -1391,10 +1702,10 @@ template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
 
 template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP >= 64) {   // narrower rows: the C fragments cost more registers than the blend saves
-    if (g_color_mma && !a.stats) return launch_fwd_mma<DP>(a, st);
+    if (!(a.flags & F_NO_COLOR_MMA) && !a.stats) return launch_fwd_mma<DP>(a, st);
   }
   if constexpr (DP == 4) {
-    if (g_raster_variant == 1) {
+    if (!(a.flags & F_ONE_PIXEL)) {
       constexpr int B2 = 128;
       const size_t smem = sizeof(Smem<DP, B2>);
       if (a.stats) rasterize_fwd2_kernel<DP, B2, true><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);  // counting only
@@ -1406,8 +1717,6 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   return launch_fwd2<DP, false>(a, st);
 }
 
-static unsigned long long* g_raster_stats = nullptr;
-static int g_cull_mode = 1;  // 0: bbox of the footprint ellipse; 1 (default): exact ellipse-vs-rectangle test
 // backward batch: wide rows also keep the tile's v_c rows (RT x DP floats) in shared memory, so the staged batches
 // are halved there to keep two CTAs per SM
 template <int DP> struct BwdBatch { static constexpr int value = DP >= 64 ? 32 : Batch<DP>::value; };
@@ -1424,20 +1733,36 @@ template <int DP, bool ABSGRAD, bool CMMA> int launch_bwd3(const RasterArgs& a, 
 }
 template <int DP, bool ABSGRAD> int launch_bwd2(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP >= 20) {   // measured: -3 % at 20 channels, -24..-29 % at 32-36, +5 % (worse) at 16
-    if (g_color_mma) return launch_bwd3<DP, ABSGRAD, true>(a, st);
+    if (!(a.flags & F_NO_COLOR_MMA)) return launch_bwd3<DP, ABSGRAD, true>(a, st);
   }
   return launch_bwd3<DP, ABSGRAD, false>(a, st);
 }
 template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
-    if (g_raster_variant == 1) {   // must match the forward variant: the two share sigma_col()'s rounding
+    if (!(a.flags & F_ONE_PIXEL)) {   // must match the forward variant: the two share sigma_col()'s rounding
       constexpr int B2 = RT2;
       const size_t smem = sizeof(Smem<DP, B2>);
       const int grid = a.C * a.tile_w * a.tile_h;
       // MINB = CTAs per SM the register allocation is capped for: 4 -> 94 registers, 6 -> 80, 7 -> 72 (no spills)
+      const int tune = bwd_tune(a.flags);
+      if (!a.abs_grad && !(a.flags & F_BWD_SHUFFLE)) {   // (absgrad sums |per-pixel gradient|: not linear, keeps the shuffle tree)
+        // RS_RASTER_BWD_TUNE: 0 (default) = 64-Gaussian batches, 4 CTAs/SM; 1 = 128-Gaussian batches, 3 CTAs/SM
+#define RS_LAUNCH_BWD3(BT, MINB)                                                                                    \
+  do {                                                                                                              \
+    const size_t smem3 = sizeof(Smem<DP, BT>) + (RT2 / 32) * sizeof(Bwd3Warp) + sizeof(Bwd3Cta);                    \
+    cudaError_t e = cudaFuncSetAttribute(rasterize_bwd3_kernel<BT, MINB>,                                           \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);                  \
+    if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }                                 \
+    rasterize_bwd3_kernel<BT, MINB><<<grid, RT2, smem3, st>>>(a);                                                   \
+  } while (0)
+        if (tune == 1) RS_LAUNCH_BWD3(128, 3);
+        else RS_LAUNCH_BWD3(64, 4);
+#undef RS_LAUNCH_BWD3
+        RS_RETURN_LAST_ERROR();
+      }
       if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4><<<grid, RT2, smem, st>>>(a);
-      else if (g_bwd2_minb == 7) rasterize_bwd2_kernel<B2, false, 7><<<grid, RT2, smem, st>>>(a);
-      else if (g_bwd2_minb == 6) rasterize_bwd2_kernel<B2, false, 6><<<grid, RT2, smem, st>>>(a);
+      else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7><<<grid, RT2, smem, st>>>(a);
+      else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6><<<grid, RT2, smem, st>>>(a);
       else rasterize_bwd2_kernel<B2, false, 4><<<grid, RT2, smem, st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
@@ -1463,25 +1788,9 @@ bool check_common(const RasterArgs& a) {
 
 extern "C" int rs_raster_padded_channels(int D) { return padded_channels(D); }
 
-// tuning knob for A/B measurements: forward kernel variant for <= 4 colour channels (0 = default)
-extern "C" void rs_raster_set_variant(int v) { g_raster_variant = v; }
-extern "C" int rs_raster_get_variant(void) { return g_raster_variant; }
-// wide colour rows (>= 32 channels): 1 (default) = tensor-core colour-gradient reduction, 0 = SIMT row walk
-extern "C" void rs_raster_set_color_mma(int on) { g_color_mma = on ? 1 : 0; }
-extern "C" void rs_raster_set_occupancy(int min_blocks) { g_bwd2_minb = (min_blocks == 6 || min_blocks == 7) ? min_blocks : 4; }
-// footprint test used by rs_pack_geom AND the compositing kernels (set it before rs_pack_geom and leave it until
-// the backward has run): 0 = padded bbox of the alpha >= 1/255 ellipse, 1 (default) = exact ellipse-vs-rectangle
-extern "C" void rs_raster_set_cull_mode(int m) { g_cull_mode = m ? 1 : 0; }
-extern "C" int rs_raster_get_cull_mode(void) { return g_cull_mode; }
-
-// Work counters for the roofline arithmetic (bench.py): while `dev_counters` (4 x u64, device, zeroed by the caller)
-// is set, forward launches with <= 4 colour channels run an instrumented kernel that adds
-// {Q, Qc, warp evaluations, blending warp evaluations} to it.  Pass NULL to switch back to the normal kernel.
-extern "C" void rs_raster_set_stats(unsigned long long* dev_counters) { g_raster_stats = dev_counters; }
-
 extern "C" int rs_pack_geom(const float* means2d, const float* conics, const float* opacities, int opac_per_cam,
                             const float* compensations, int C, int N, const float* ray_ts, const float* ray_planes,
-                            const float* normals, const int32_t* radii, float* geom, void* stream) {
+                            const float* normals, const int32_t* radii, float* geom, int flags, void* stream) {
   RsSpan span__("rs_pack_geom", stream);
   if (C < 0 || N < 0) return RS_ERR_BAD_ARG;
   const long long n_elems = (long long)C * N;
@@ -1489,7 +1798,7 @@ extern "C" int rs_pack_geom(const float* means2d, const float* conics, const flo
   if (!means2d || !conics || !opacities || !ray_ts || !ray_planes || !normals || !geom) return RS_ERR_BAD_ARG;
   pack_geom_kernel<<<rs_div_up(n_elems, 256), 256, 0, (cudaStream_t)stream>>>(
       (const float2*)means2d, conics, opacities, opac_per_cam, compensations, N, ray_ts, (const float2*)ray_planes,
-      normals, (const int2*)radii, n_elems, g_cull_mode, (float4*)geom);
+      normals, (const int2*)radii, n_elems, (flags & F_CULL_BBOX) ? 0 : 1, (float4*)geom);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -1536,7 +1845,8 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
                                 int height, int tile_w, int tile_h, const int32_t* tile_offsets,
                                 const int32_t* flatten_ids, long long M, float* out_colors, float* out_alphas,
                                 float* out_expected_depths, float* out_median_depths, float* out_normals,
-                                float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream) {
+                                float* out_transmittance, int32_t* last_ids, int32_t* median_ids, int flags,
+                                unsigned long long* stats, void* stream) {
   RsSpan span__("rs_rasterize_fwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
@@ -1544,11 +1854,12 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
   a.ed_channel = ed_channel;
-  a.exact_cull = g_cull_mode;
+  a.exact_cull = (flags & F_CULL_BBOX) ? 0 : 1;
+  a.flags = flags;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
-  a.stats = g_raster_stats;
+  a.stats = stats;
   if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
     return RS_ERR_BAD_ARG;
   if (ed_channel >= D) return RS_ERR_BAD_ARG;
@@ -1570,7 +1881,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
                                 const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
                                 const float* v_colors, const float* v_alphas, const float* v_expected_depths,
                                 const float* v_median_depths, const float* v_normals, float* geom_grad,
-                                float* color_grad, float* abs_grad, void* stream) {
+                                float* color_grad, float* abs_grad, int flags, void* stream) {
   RsSpan span__("rs_rasterize_bwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
@@ -1578,7 +1889,8 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
   a.C = C; a.N = N; a.W = width; a.H = height; a.tile_w = tile_w; a.tile_h = tile_h; a.D = D;
   a.color_per_cam = (color_per_cam || C == 1) ? 1 : 0;
   a.ed_channel = ed_channel;
-  a.exact_cull = g_cull_mode;
+  a.exact_cull = (flags & F_CULL_BBOX) ? 0 : 1;
+  a.flags = flags;
   a.offsets = tile_offsets; a.flatten_ids = flatten_ids; a.M = (int)M;
   a.out_colors = (float*)out_colors;
   a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;

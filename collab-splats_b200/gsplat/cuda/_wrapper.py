@@ -14,6 +14,7 @@ collab-splats never uses (packed=True, sparse_grad, covars, non-pinhole cameras,
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -34,6 +35,11 @@ ISECT_SORT_METHOD = "presort"
 #   "chunk": per-camera depth argsort + chunked counting sort (csrc/chunksort.cu), no radix passes over the pairs
 #            (measured slower: scattered 12-byte stores, profiles/r01_chunk_ab.txt);  "tile": csrc/tilesort.cu
 ISECT_PIPELINE = "radix"
+# Compositing options (backend.RS_RASTER_* bits, 0 = defaults) and optional work counters (a 4 x int64 device tensor,
+# <= 4 channels) that rasterize_to_pixels passes with every call.  They are read when the forward runs and travel
+# with its saved tensors, so the backward of a render always uses the flags its forward used.
+RASTER_FLAGS = int(os.environ.get("RADE_RASTER_FLAGS", "0"), 0)   # (the environment variable only seeds the default)
+RASTER_STATS = None
 # Set by radegs_b200.multiview.ShGradExchange while a camera-sharded multi-GPU step runs: the backward of the
 # fused SH colours then publishes per-camera colour gradients instead of producing the coefficient gradient.
 SH_GRAD_SINK = None
@@ -549,6 +555,8 @@ class _RasterizeToPixels(torch.autograd.Function):
         rows = C * N if color_per_cam else N
         tile_h, tile_w = isect_offsets.shape[1:]
         M = flatten_ids.numel()
+        flags = int(RASTER_FLAGS)
+        stats = RASTER_STATS
         f32 = dict(device=dev, dtype=torch.float32)
         geom = torch.empty(C * N, 16, **f32)
         out_colors = torch.empty(C, height, width, D, **f32)
@@ -563,7 +571,7 @@ class _RasterizeToPixels(torch.autograd.Function):
             st = _be.stream_ptr(dev)
             _be.check(lib.rs_pack_geom(_be.ptr(means2d), _be.ptr(conics), _be.ptr(opacities), int(opac_per_cam),
                                        _be.ptr(compensations), C, N, _be.ptr(ray_ts), _be.ptr(ray_planes),
-                                       _be.ptr(normals), None, _be.ptr(geom), st), "rs_pack_geom")
+                                       _be.ptr(normals), None, _be.ptr(geom), flags, st), "rs_pack_geom")
             if DP == D:
                 colors_p = colors
             else:
@@ -573,11 +581,11 @@ class _RasterizeToPixels(torch.autograd.Function):
                 _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, ed_channel, _be.ptr(backgrounds), _be.ptr(Ks),
                 C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
                 _be.ptr(out_colors), _be.ptr(out_alphas), _be.ptr(out_dexp), _be.ptr(out_dmed), _be.ptr(out_normals),
-                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), st), "rs_rasterize_fwd")
+                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), flags, _be.ptr(stats), st), "rs_rasterize_fwd")
         ctx.save_for_backward(geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids,
                               median_ids, opacities, compensations, out_colors if ed_channel >= 0 else None)
         ctx.cfg = (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad,
-                   ed_channel, colors.shape)
+                   ed_channel, colors.shape, flags)
         ctx.means2d_ref = means2d if absgrad else None
         ctx.mark_non_differentiable(last_ids, median_ids)
         ctx.set_materialize_grads(False)   # missing output gradients arrive as None (handled by z() below)
@@ -589,7 +597,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         (geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids, median_ids, opacities,
          compensations, out_colors) = ctx.saved_tensors
         (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, ed_channel,
-         colors_shape) = ctx.cfg
+         colors_shape, flags) = ctx.cfg
         dev = geom.device
         f32 = dict(device=dev, dtype=torch.float32)
 
@@ -620,7 +628,7 @@ class _RasterizeToPixels(torch.autograd.Function):
                 C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
                 _be.ptr(out_colors), _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), _be.ptr(v_colors),
                 _be.ptr(v_alphas), _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad),
-                _be.ptr(color_grad), _be.ptr(abs_grad), st), "rs_rasterize_bwd")
+                _be.ptr(color_grad), _be.ptr(abs_grad), flags, st), "rs_rasterize_bwd")
             _be.check(lib.rs_unpack_geom_grad(
                 _be.ptr(geom_grad), _be.ptr(geom), _be.ptr(abs_grad), C, N, _be.ptr(opacities), int(opac_per_cam),
                 _be.ptr(compensations), _be.ptr(v_means2d), _be.ptr(v_abs), _be.ptr(v_conics), _be.ptr(v_opac),

@@ -61,18 +61,11 @@ _SIGNATURES = {
     "rs_sort_set_window": (None, [_i]),
     "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_raster_padded_channels": (_i, [_i]),
-    "rs_raster_set_stats": (None, [_p]),
-    "rs_raster_set_variant": (None, [_i]),
-    "rs_raster_get_variant": (_i, []),
-    "rs_raster_set_color_mma": (None, [_i]),
-    "rs_raster_set_occupancy": (None, [_i]),
-    "rs_raster_set_cull_mode": (None, [_i]),
-    "rs_raster_get_cull_mode": (_i, []),
-    "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p]),
     "rs_pack_colors": (_i, [_p, _ll, _i, _i, _p, _p]),
-    "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_p]),
+    "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_i, _p, _p]),
     "rs_rasterize_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 4 + [_p] * 5
-                         + [_p, _p, _p] + [_p]),
+                         + [_p, _p, _p] + [_i, _p]),
     "rs_unpack_geom_grad": (_i, [_p, _p, _p, _i, _i, _p, _i, _p] + [_p] * 9 + [_i, _i, _p]),
     "rs_sh_colors_fwd": (_i, [_i, _i, _i, _i] + [_p] * 6 + [_p]),
     "rs_sh_colors_bwd": (_i, [_i, _i, _i, _i] + [_p] * 5 + [_i] + [_p] * 3 + [_p]),
@@ -99,6 +92,17 @@ _SIGNATURES = {
     "rs_feature_hidden_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
+
+# per-call compositing options (include/rade_b200.h)
+RS_RASTER_CULL_BBOX = 0x1
+RS_RASTER_ONE_PIXEL = 0x2
+RS_RASTER_NO_COLOR_MMA = 0x4
+RS_RASTER_BWD_SHUFFLE = 0x8
+
+
+def RS_RASTER_BWD_TUNE(x: int) -> int:
+    return (x & 0xF) << 8
+
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES) + ("rs_set_last_cuda_error", "rs_count_launches", "rs_timing_begin",
                                           "rs_timing_end")

@@ -129,35 +129,33 @@ int rs_argsort_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32_t*
  * Inputs are first packed: geom[C*N,16] (rs_pack_geom) and colours padded to DP = rs_raster_padded_channels(D)
  * channels (rs_pack_colors; colours may be [C*N,D] (color_per_cam=1) or [N,D] shared by all cameras). */
 int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the host */
-/* Work counters for roofline arithmetic: while set, forward launches with <= 4 channels run an instrumented
- * kernel adding {Q visited pairs, Qc blended pairs, warp evaluations, blending warp evaluations} (4 x u64). */
-void rs_raster_set_stats(unsigned long long* dev_counters);
-/* compositing variant for <= 4 colour channels, forward AND backward (set it before the forward, leave it until the
- * backward has run): 0 = one pixel per lane (8x4 block per warp), 1 = two pixels per lane (8x8 block per warp) */
-void rs_raster_set_variant(int variant);
-int rs_raster_get_variant(void);
-/* wide colour rows (>= 32 channels): 1 (default) = colour gradients reduced on the tensor cores (mma.sync TF32 with
- * head/tail operand splitting, fp32-accurate), 0 = SIMT row walk.  A/B knob. */
-void rs_raster_set_color_mma(int on);
-void rs_raster_set_occupancy(int min_blocks); /* tuning knob: register cap of the 2-px backward (4, 6 or 7 CTAs/SM) */
-/* footprint (alpha >= 1/255) test the records are packed for and the kernels apply per (warp, Gaussian): 0 = padded
- * bbox of the footprint ellipse, 1 (default) = exact ellipse-vs-rectangle test.  Both are conservative, so results
- * do not depend on it.  Set it before rs_pack_geom and leave it until the backward has run. */
-void rs_raster_set_cull_mode(int mode);
-int rs_raster_get_cull_mode(void);
+/* Per-call compositing options (`flags` of rs_pack_geom / rs_rasterize_fwd / rs_rasterize_bwd; 0 = the defaults).
+ * There is no process-global state: a render passes the SAME flags to its pack, forward and backward calls (the
+ * torch layer stores them with the saved tensors), so concurrent callers cannot disturb each other.  Every
+ * combination gives the same results (all footprint tests are conservative, all reductions fp32-accurate); the
+ * non-default ones exist for A/B measurements and tests. */
+#define RS_RASTER_CULL_BBOX 0x1      /* footprint test: padded bbox of the alpha >= 1/255 ellipse instead of the exact
+                                        ellipse-vs-rectangle test */
+#define RS_RASTER_ONE_PIXEL 0x2      /* <= 4 channels: one pixel per lane (8x4 block per warp) instead of two (8x8) */
+#define RS_RASTER_NO_COLOR_MMA 0x4   /* >= 20 channels: SIMT colour blend / colour-gradient reduction instead of mma.sync */
+#define RS_RASTER_BWD_SHUFFLE 0x8    /* <= 4 channels backward: shuffle-tree reduction instead of the mma.sync contraction */
+#define RS_RASTER_BWD_TUNE(x) (((x) & 0xf) << 8)   /* backward occupancy / batch variant (0 = default), see rasterize.cu */
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
                  const float* compensations /* [C*N] or NULL: effective opacity = opacity * compensation */,
                  int C, int N, const float* ray_ts, const float* ray_planes, const float* normals,
-                 const int32_t* radii /* NULL ok */, float* geom /* [C*N,16] */, void* stream);
+                 const int32_t* radii /* NULL ok */, float* geom /* [C*N,16] */, int flags, void* stream);
 int rs_pack_colors(const float* colors, long long rows, int D, int DP, float* out, void* stream);
-/* ed_channel >= 0: that output channel is divided by max(alpha, 1e-10) (the "ED" render modes); -1: none. */
+/* ed_channel >= 0: that output channel is divided by max(alpha, 1e-10) (the "ED" render modes); -1: none.
+ * stats (NULL ok; <= 4 channels only): 4 x u64 device counters, zeroed by the caller; the launch then runs an instrumented
+ * kernel that adds {Q pairs a per-pixel loop visits, Qc blended pairs, warp evaluations, blending warp evaluations}. */
 int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_per_cam, int D, int ed_channel,
                      const float* backgrounds /* [C,D] or NULL */, const float* Ks, int C, int N, int width,
                      int height, int tile_w, int tile_h, const int32_t* tile_offsets, const int32_t* flatten_ids,
                      long long M, float* out_colors /* [C,H,W,D] */, float* out_alphas /* [C,H,W] */,
                      float* out_expected_depths, float* out_median_depths, float* out_normals /* [C,H,W,3] */,
-                     float* out_transmittance, int32_t* last_ids, int32_t* median_ids, void* stream);
+                     float* out_transmittance, int32_t* last_ids, int32_t* median_ids, int flags,
+                     unsigned long long* stats, void* stream);
 /* Gradient record geom_grad[C*N,16] = (S v_sigma*dx, S v_sigma*dy | ga gb gc | S v_sigma | g_ray_t g_rpx g_rpy |
  * gnx gny gnz | colour 0..3), S = sum over blended pixels; rs_unpack_geom_grad turns the three moments into the
  * means2d and opacity gradients (per-Gaussian linear maps with the conic / ray plane / opacity of `geom`);
@@ -169,7 +167,7 @@ int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_pe
                      const float* out_colors, const float* transmittance, const int32_t* last_ids,
                      const int32_t* median_ids, const float* v_colors, const float* v_alphas,
                      const float* v_expected_depths, const float* v_median_depths, const float* v_normals,
-                     float* geom_grad, float* color_grad, float* abs_grad, void* stream);
+                     float* geom_grad, float* color_grad, float* abs_grad, int flags, void* stream);
 /* Splits the gradient record into the per-input gradients; undoes the opacity * compensation fusion
  * (v_compensations[C,N] = go * opacity, v_opacities = go * compensation, summed over cameras when the
  * opacities are [N]); v_colors4 (NULL ok) receives the colour gradient when the colours have <= 4 channels. */

@@ -549,9 +549,13 @@ def rasterization(
     sh_degree: Optional[int] = None, tile_size: int = 16, backgrounds: Optional[Tensor] = None,
     render_mode: str = "RGB", rasterize_mode: str = "classic", return_depth_normal: bool = False,
     return_aux: bool = False, tile_window: Optional[Tuple[int, int, int, int]] = None,
+    compositor: str = "torch", threads: Optional[int] = None,
 ):
     """Restates ``gsplat.rendering.rasterization`` for the options the reference uses
-    (call site rade_gs_model.py:439-465): packed=False, pinhole, 3DGS."""
+    (call site rade_gs_model.py:439-465): packed=False, pinhole, 3DGS.
+
+    ``compositor="c"`` runs the per-tile compositing stage (forward and backward) through the C restatement
+    (oracle/raster_oracle.c, ``threads`` host threads) instead of the PyTorch one; everything else is unchanged."""
     assert render_mode in ("RGB", "D", "ED", "RGB+D", "RGB+ED")
     assert rasterize_mode in ("classic", "antialiased")
     C, N = viewmats.shape[0], means.shape[0]
@@ -581,9 +585,16 @@ def rasterization(
     TH = math.ceil(height / tile_size)
     tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, TW, TH)
     isect_offsets = isect_offset_encode(isect_ids, C, TW, TH)
-    res = rasterize_to_pixels(means2d, conics, cols, opac, ray_ts, ray_planes, normals, Ks, width, height,
-                              tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds, return_aux=True,
-                              tile_window=tile_window)
+    if compositor == "c":
+        from . import raster_oracle as _RO
+        res = _RO.rasterize_to_pixels(means2d, conics, cols, opac, ray_ts, ray_planes, normals, Ks, width, height,
+                                      tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
+                                      return_aux=True, threads=threads)
+    else:
+        assert compositor == "torch", compositor
+        res = rasterize_to_pixels(means2d, conics, cols, opac, ray_ts, ray_planes, normals, Ks, width, height,
+                                  tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds, return_aux=True,
+                                  tile_window=tile_window)
     render_colors, render_alphas, exp_d, med_d, nrm, aux = res
     if render_mode in ("ED", "RGB+ED"):
         render_colors = torch.cat([render_colors[..., :-1],

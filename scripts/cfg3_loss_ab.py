@@ -1,6 +1,7 @@
 import json, sys
 sys.path.insert(0, "collab-splats_b200"); sys.path.insert(0, ".")
 import torch
+from gsplat.cuda import _wrapper as W
 from radegs_b200 import backend as be, scenes
 from gsplat.rendering import rasterization
 dev = torch.device("cuda:0"); lib = be.load()
@@ -16,7 +17,7 @@ def step(kind):
     else: ((o[0] * w).sum() + o[2].mean() + o[3].mean() + o[4].mean()).backward()
 for kind in ("sq", "rand"):
     for mode in (0, 1):
-        lib.rs_raster_set_color_mma(mode)
+        W.RASTER_FLAGS = 0 if mode else be.RS_RASTER_NO_COLOR_MMA
         for _ in range(3): step(kind)
         lib.rs_timing_enable(1)
         for _ in range(5): step(kind)

@@ -25,9 +25,13 @@ def step():
     sum((a * b).sum() for a, b in zip(o[:5], cot)).backward()
     return [t.detach() for t in o[:5]], [t.grad.clone() for t in p]
 ref = None
-default = lib.rs_raster_get_variant()
-for variant, cull, occ in ((0, 1, 4), (1, 1, 4), (1, 1, 6), (1, 1, 7), (1, 1, 4), (1, 1, 6), (1, 1, 7)):
-    lib.rs_raster_set_variant(variant); lib.rs_raster_set_cull_mode(cull); lib.rs_raster_set_occupancy(occ)
+from gsplat.cuda import _wrapper as W
+VARIANTS = (("1px", be.RS_RASTER_ONE_PIXEL), ("2px shuffle bwd", be.RS_RASTER_BWD_SHUFFLE),
+            ("2px mma bwd (default)", 0), ("2px mma bwd 128/3", be.RS_RASTER_BWD_TUNE(1)),
+            ("2px shuffle bwd", be.RS_RASTER_BWD_SHUFFLE), ("2px mma bwd (default)", 0),
+            ("2px mma bwd 128/3", be.RS_RASTER_BWD_TUNE(1)))
+for name, flags in VARIANTS:
+    W.RASTER_FLAGS = flags
     for _ in range(3): o, g = step()
     lib.rs_timing_enable(1)
     for _ in range(10): o, g = step()
@@ -36,6 +40,6 @@ for variant, cull, occ in ((0, 1, 4), (1, 1, 4), (1, 1, 6), (1, 1, 7), (1, 1, 4)
     if ref is None: ref = (o, g)
     err = max(float((a - b).abs().max()) for a, b in zip(o, ref[0]))
     gerr = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g, ref[1]))
-    print(f"variant {variant} cull {cull} occ {occ}: sh_fwd {s['rs_sh_colors_fwd'][0] / 10:.4f} sh_bwd {s['rs_sh_colors_bwd'][0] / 10:.4f} emit {s['rs_isect_emit_ordered'][0] / 10:.4f} fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
+    print(f"{name:24s}: sh_fwd {s['rs_sh_colors_fwd'][0] / 10:.4f} sh_bwd {s['rs_sh_colors_bwd'][0] / 10:.4f} emit {s['rs_isect_emit_ordered'][0] / 10:.4f} fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
           f"unpack {s['rs_unpack_geom_grad'][0] / 10:.4f} ms   max|out diff vs first| {err:.2e}  max rel grad diff {gerr:.2e}")
-lib.rs_raster_set_variant(default); lib.rs_raster_set_cull_mode(1); lib.rs_raster_set_occupancy(4)
+W.RASTER_FLAGS = 0

@@ -1,10 +1,11 @@
 """A/B of the wide-row (rade-features, 3 + 64 channels) backward at BASELINE config 3: tensor-core colour-gradient
-reduction (rs_raster_set_color_mma(1), default) vs the SIMT row walk (0); gradients compared between the two."""
+reduction (default; RS_RASTER_NO_COLOR_MMA switches it off) vs the SIMT row walk (0); gradients compared between the two."""
 import json, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "collab-splats_b200")); sys.path.insert(0, str(ROOT))
 import torch
+from gsplat.cuda import _wrapper as W
 from radegs_b200 import backend as be, scenes
 from gsplat.rendering import rasterization
 
@@ -30,7 +31,7 @@ def step():
 out = {"channels": 3 + NF + 1}
 grads = {}
 for mode in (0, 1, 0, 1):
-    lib.rs_raster_set_color_mma(mode)
+    W.RASTER_FLAGS = 0 if mode else be.RS_RASTER_NO_COLOR_MMA
     for _ in range(3): step()
     lib.rs_timing_enable(1)
     for _ in range(5): step()
@@ -41,5 +42,5 @@ for mode in (0, 1, 0, 1):
 d = (grads[1] - grads[0]).abs().max().item()
 out["max_abs_diff_color_grad"] = d
 out["color_grad_scale"] = grads[0].abs().max().item()
-lib.rs_raster_set_color_mma(1)
+W.RASTER_FLAGS = 0
 print(json.dumps(out, indent=1))

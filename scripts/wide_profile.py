@@ -4,12 +4,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "collab-splats_b200")); sys.path.insert(0, str(ROOT))
 import torch
+from gsplat.cuda import _wrapper as W
 from radegs_b200 import backend as be, scenes
 from gsplat.rendering import rasterization
 dev = torch.device("cuda:0")
 lib = be.load()
 if len(sys.argv) > 1:
-    lib.rs_raster_set_color_mma(int(sys.argv[1]))
+    W.RASTER_FLAGS = 0 if int(sys.argv[1]) else be.RS_RASTER_NO_COLOR_MMA
 cfg = scenes.BASELINE_CONFIGS[3]
 gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
 p = [t.to(dev).requires_grad_(True) for t in scenes.activate(gs, None)]

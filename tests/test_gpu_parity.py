@@ -255,20 +255,22 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
 
 @pytest.fixture
 def raster_variant(request):
-    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane; +10:
-    with the bbox footprint test instead of the exact ellipse-vs-rectangle one) for the duration of a test and
-    restores the library defaults afterwards."""
+    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane, backward
+    reduced on the tensor cores, 2: 8x8 with the shuffle-tree backward; +10: with the bbox footprint test instead of the
+    exact ellipse-vs-rectangle one) through the per-call flags for the duration of a test."""
     from radegs_b200 import backend as be
-    lib = be.load()
-    default, default_cull = lib.rs_raster_get_variant(), lib.rs_raster_get_cull_mode()
-    lib.rs_raster_set_variant(request.param % 10)
-    lib.rs_raster_set_cull_mode(0 if request.param >= 10 else 1)
-    yield request.param % 10
-    lib.rs_raster_set_variant(default)
-    lib.rs_raster_set_cull_mode(default_cull)
+    from gsplat.cuda import _wrapper as W
+    v = request.param % 10
+    flags = {0: be.RS_RASTER_ONE_PIXEL, 1: 0, 2: be.RS_RASTER_BWD_SHUFFLE}[v]
+    if request.param >= 10:
+        flags |= be.RS_RASTER_CULL_BBOX
+    old = W.RASTER_FLAGS
+    W.RASTER_FLAGS = flags
+    yield v
+    W.RASTER_FLAGS = old
 
 
-@pytest.mark.parametrize("raster_variant", [0, 1, 10, 11], indirect=True)
+@pytest.mark.parametrize("raster_variant", [0, 1, 2, 10, 11], indirect=True)
 @pytest.mark.parametrize("D,views,w,h,bg,n", [(3, 1, 160, 96, False, 2500), (4, 2, 100, 70, True, 2500),
                                                (17, 1, 96, 64, False, 2500), (67, 1, 64, 48, True, 2500),
                                                (8, 1, 64, 64, False, 2500),
@@ -828,11 +830,11 @@ def test_chunked_counting_sort_nothing_visible(cuda_dev):
 
 
 def test_forward_two_pixels_per_lane_variant(cuda_dev):
-    """The experimental forward variant (8x8 pixels per warp, two per lane; rs_raster_set_variant(1)) against the
-    oracle and against the default kernel, incl. multi-batch tiles, image edges and a background."""
+    """The two-pixels-per-lane forward (8x8 pixels per warp, the default) against the oracle and against the
+    one-pixel-per-lane kernel (RS_RASTER_ONE_PIXEL), incl. multi-batch tiles, image edges and a background."""
+    from gsplat.cuda import _wrapper as W
     from gsplat.cuda._wrapper import rasterize_to_pixels
     from radegs_b200 import backend as be
-    lib = be.load()
     for (n, w, h, views) in ((2500, 150, 90, 2), (9000, 64, 48, 1)):
         cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views)
         inp, offs, flat = _raster_inputs(cfg, gs, vm, Ks, 4)
@@ -843,14 +845,14 @@ def test_forward_two_pixels_per_lane_variant(cuda_dev):
         d = {k: v.to(cuda_dev) for k, v in inp.items()}
         outs = []
         try:
-            for variant in (0, 1):
-                lib.rs_raster_set_variant(variant)
+            for flags in (be.RS_RASTER_ONE_PIXEL, 0):
+                W.RASTER_FLAGS = flags
                 outs.append(rasterize_to_pixels(d["means2d"], d["conics"], d["colors"], d["opacities"], w, h, 16,
                                                 offs.to(cuda_dev), flat.to(cuda_dev), backgrounds=bg.to(cuda_dev),
                                                 ray_ts=d["ray_ts"], ray_planes=d["ray_planes"], normals=d["normals"],
                                                 Ks=Ks.to(cuda_dev), return_ids=True))
         finally:
-            lib.rs_raster_set_variant(0)
+            W.RASTER_FLAGS = 0
         keep = ~ref[5]["fragile"]
         for i, nm in enumerate(["colors", "alphas", "expected_depths", "median_depths", "normals"]):
             ok, msg = close_report(nm, outs[1][i], ref[i], mask=keep)
