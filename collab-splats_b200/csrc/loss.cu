@@ -10,8 +10,11 @@
 // the three loss sums (block reduction + one atomicAdd per block) and scatters the depth gradients with
 // float atomics (8 per interior pixel).  HBM-bound: ~90 B per pixel.
 #include "common.cuh"
+#include "dn_stencil.cuh"
 
 namespace {
+using rs::V3;
+using rs::dn_term;
 
 constexpr int LB = 256;
 
@@ -34,43 +37,6 @@ struct LossArgs {
   float* v_med_depth;       // [H,W]  (zero-initialised by the caller)
   float* v_normals;         // [H,W,3]
 };
-
-struct V3 { float x, y, z; };
-__device__ __forceinline__ V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
-
-// one depth map: returns err contribution, accumulates v_normal (rendered) and scatters v_depth
-__device__ __forceinline__ float dn_term(const float* __restrict__ depth, float* __restrict__ v_depth, int x, int y,
-                                         int W, int H, float ifx, float ify, V3 N, float g, V3& vN) {
-  if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return 1.0f;  // border normals are 0 -> err = 1, no gradient
-  const float cx = 0.5f * W, cy = 0.5f * H;
-  const float rxm = (x - 0.5f - cx) * ifx, rx0 = (x + 0.5f - cx) * ifx, rxp = (x + 1.5f - cx) * ifx;
-  const float rym = (y - 0.5f - cy) * ify, ry0 = (y + 0.5f - cy) * ify, ryp = (y + 1.5f - cy) * ify;
-  const size_t p = (size_t)y * W + x;
-  const float du = __ldg(depth + p - W), dd = __ldg(depth + p + W), dl = __ldg(depth + p - 1), dr = __ldg(depth + p + 1);
-  // d_row = P(x,y+1) - P(x,y-1);  d_col = P(x+1,y) - P(x-1,y);  P = depth * (rx, ry, 1)
-  const V3 a = {(dd - du) * rx0, dd * ryp - du * rym, dd - du};
-  const V3 b = {dr * rxp - dl * rxm, (dr - dl) * ry0, dr - dl};
-  const V3 c = cross3(a, b);
-  const float len = sqrtf(c.x * c.x + c.y * c.y + c.z * c.z);
-  const float inv = 1.0f / fmaxf(len, 1e-12f);
-  const V3 n = {c.x * inv, c.y * inv, c.z * inv};
-  const float dot = N.x * n.x + N.y * n.y + N.z * n.z;
-  // gradients: err = 1 - N.n, upstream weight g
-  vN.x -= g * n.x; vN.y -= g * n.y; vN.z -= g * n.z;
-  if (len > 1e-12f) {
-    const V3 vn = {-g * N.x, -g * N.y, -g * N.z};
-    const float nd = n.x * vn.x + n.y * vn.y + n.z * vn.z;
-    const V3 vc = {(vn.x - n.x * nd) * inv, (vn.y - n.y * nd) * inv, (vn.z - n.z * nd) * inv};
-    const V3 va = cross3(b, vc);   // d(a x b)/da ^T vc = b x vc
-    const V3 vb = cross3(vc, a);   // d(a x b)/db ^T vc = vc x a
-    // a depends on dd (+) and du (-); b on dr (+) and dl (-)
-    atomicAdd(v_depth + p + W, va.x * rx0 + va.y * ryp + va.z);
-    atomicAdd(v_depth + p - W, -(va.x * rx0 + va.y * rym + va.z));
-    atomicAdd(v_depth + p + 1, vb.x * rxp + vb.y * ry0 + vb.z);
-    atomicAdd(v_depth + p - 1, -(vb.x * rxm + vb.y * ry0 + vb.z));
-  }
-  return 1.0f - dot;
-}
 
 __global__ void __launch_bounds__(LB) rade_loss_kernel(const LossArgs a) {
   __shared__ float s_red[4][LB / 32];

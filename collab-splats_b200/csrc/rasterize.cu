@@ -1405,16 +1405,18 @@ constexpr B3SigTab b3_make_sig() {
 }
 __device__ const B3SigTab g_b3_sig = b3_make_sig();
 
-struct Bwd3Warp {                          // per-warp shared memory
-  float4 park[B3_PEND * B3_PSTRIDE];       // [g][pixel lane] = (vis h0, vis h1, v_sigma h0, v_sigma h1)
+struct Bwd3Warp {                          // per-warp shared memory.  Everything is laid out in 8-byte pairs: measured on
+                                           // B200, LDS.64 / STS.64 move 128 B/clk/SM but LDS.128 only 64 (scripts/ubench)
+  float2 pvis[B3_PEND * B3_PSTRIDE];       // [g][pixel lane] = vis of pixels (h0, h1)
+  float2 psig[B3_PEND * B3_PSTRIDE];       // [g][pixel lane] = v_sigma of pixels (h0, h1)
   float4 meta[B3_PEND];                    // (x_g - rcx, y_g - rcy, flatten id bits, -)
   float mom[B3_PEND * B3_MSTRIDE];         // [g][column] raw moments, transposed out of the C fragments
-  float4 cah[8 * 20];                      // TF32 heads of the "vis" constants: [k step][lane < 20] = (a0, a1, a2, a3)
-  float4 cal[8 * 20];                      // their tails
-  float4 zero;                             // what the lanes without constant rows read
+  float2 cah[2][8 * 20];                   // TF32 heads of the "vis" constants: [a0 a1 | a2 a3][k step][lane < 20]
+  float2 cal[2][8 * 20];                   // their tails
+  float2 zero;                             // what the lanes without constant rows read
 };
 struct Bwd3Cta {                           // per-CTA shared memory
-  float4 sig[8 * 12];                      // copy of g_b3_sig
+  float2 sig[2][8 * 12];                   // g_b3_sig as pairs: [a0 a1 | a2 a3][k step][lane < 12]
 };
 
 __device__ __forceinline__ void b3_split(float x, unsigned& hi, unsigned& lo) {
@@ -1422,33 +1424,46 @@ __device__ __forceinline__ void b3_split(float x, unsigned& hi, unsigned& lo) {
   lo = __float_as_uint(x - __uint_as_float(hi)); // exact remainder; the tensor core reads its leading 11 bits
 }
 
-__device__ __forceinline__ void bwd3_flush(Bwd3Warp& w, const float4* __restrict__ sig_tab, int n,
-                                           float* __restrict__ geom_grad, int lane) {
+__device__ __forceinline__ void bwd3_flush(Bwd3Warp& w, const Bwd3Cta& wc, int n, float* __restrict__ geom_grad,
+                                           int lane) {
   const int gid = lane >> 2, tig = lane & 3;
   __syncwarp();   // the parked rows are complete
-  float cv[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
-  const float4* prow = w.park + gid * B3_PSTRIDE + tig;
-  // lanes without rows (gid >= 5, gid >= 3) read a quad of zeros instead (stride 0): the loop body stays branch free
-  const float4* pch = lane < 20 ? w.cah + lane : &w.zero;
-  const float4* pcl = lane < 20 ? w.cal + lane : &w.zero;
-  const float4* pcg = lane < 12 ? sig_tab + lane : &w.zero;
-  const int sv = lane < 20 ? 20 : 0, sg = lane < 12 ? 12 : 0;
+  // five independent accumulator chains (one per product), 8 k steps deep each, summed at the end: the HMMAs of one
+  // chain are ~30 cycles apart, so a single chain per group would serialise 24 of them
+  float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  const float2* pv = w.pvis + gid * B3_PSTRIDE + tig;
+  const float2* ps = w.psig + gid * B3_PSTRIDE + tig;
+  // lanes without rows (gid >= 5, gid >= 3) read a pair of zeros instead (stride 0): the loop body stays branch free
+  const bool hv = lane < 20, hs = lane < 12;
+  const float2* ph0 = hv ? w.cah[0] + lane : &w.zero;
+  const float2* ph1 = hv ? w.cah[1] + lane : &w.zero;
+  const float2* pl0 = hv ? w.cal[0] + lane : &w.zero;
+  const float2* pl1 = hv ? w.cal[1] + lane : &w.zero;
+  const float2* pg0 = hs ? wc.sig[0] + lane : &w.zero;
+  const float2* pg1 = hs ? wc.sig[1] + lane : &w.zero;
+  const int sv = hv ? 20 : 0, sg = hs ? 12 : 0;
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const float4 p = prow[4 * ks];   // Gaussian gid, pixel lane 4 ks + tig: k = tig is its pixel h0, k = tig + 4 its pixel h1
-    const float4 ch = pch[ks * sv], cl = pcl[ks * sv], cg = pcg[ks * sg];
+    // Gaussian gid, pixel lane 4 ks + tig: k = tig is its pixel h0, k = tig + 4 its pixel h1
+    const float2 v = pv[4 * ks], sgm = ps[4 * ks];
+    const float2 h01 = ph0[ks * sv], h23 = ph1[ks * sv], l01 = pl0[ks * sv], l23 = pl1[ks * sv];
+    const float2 g01 = pg0[ks * sg], g23 = pg1[ks * sg];
     unsigned vh0, vl0, vh1, vl1, sh0, sl0, sh1, sl1;
-    b3_split(p.x, vh0, vl0); b3_split(p.y, vh1, vl1);
-    b3_split(p.z, sh0, sl0); b3_split(p.w, sh1, sl1);
-    const unsigned ah[4] = {__float_as_uint(ch.x), __float_as_uint(ch.y), __float_as_uint(ch.z), __float_as_uint(ch.w)};
-    const unsigned al[4] = {__float_as_uint(cl.x), __float_as_uint(cl.y), __float_as_uint(cl.z), __float_as_uint(cl.w)};
-    const unsigned as[4] = {__float_as_uint(cg.x), __float_as_uint(cg.y), __float_as_uint(cg.z), __float_as_uint(cg.w)};
-    mma_tf32_16x8x8(cv, ah, vh0, vh1);
-    mma_tf32_16x8x8(cv, al, vh0, vh1);
-    mma_tf32_16x8x8(cv, ah, vl0, vl1);
-    mma_tf32_16x8x8(cs, as, sh0, sh1);
-    mma_tf32_16x8x8(cs, as, sl0, sl1);
+    b3_split(v.x, vh0, vl0); b3_split(v.y, vh1, vl1);
+    b3_split(sgm.x, sh0, sl0); b3_split(sgm.y, sh1, sl1);
+    const unsigned ah[4] = {__float_as_uint(h01.x), __float_as_uint(h01.y), __float_as_uint(h23.x), __float_as_uint(h23.y)};
+    const unsigned al[4] = {__float_as_uint(l01.x), __float_as_uint(l01.y), __float_as_uint(l23.x), __float_as_uint(l23.y)};
+    const unsigned as[4] = {__float_as_uint(g01.x), __float_as_uint(g01.y), __float_as_uint(g23.x), __float_as_uint(g23.y)};
+    mma_tf32_16x8x8(c1, ah, vh0, vh1);
+    mma_tf32_16x8x8(s1, as, sh0, sh1);
+    mma_tf32_16x8x8(c2, al, vh0, vh1);
+    mma_tf32_16x8x8(s2, as, sl0, sl1);
+    mma_tf32_16x8x8(c3, ah, vl0, vl1);
   }
+  float cv[4], cs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { cv[i] = c1[i] + (c2[i] + c3[i]); cs[i] = s1[i] + s2[i]; }
   // C fragments -> mom[g][column]: (c0, c1) = row gid, (c2, c3) = row gid + 8 of Gaussians 2 tig, 2 tig + 1
   float* const m = w.mom;
   if (gid < 5) {
@@ -1560,7 +1575,7 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
   {
     const int gid = lane >> 2, tig = lane & 3;
     const float u_own = (float)(lane & 7) - 3.5f;
-    float4* sc = w.park;   // scratch [lane][5 float4]: 10 columns x 2 pixels
+    float4* sc = reinterpret_cast<float4*>(w.pvis);   // scratch [lane][5 float4]: 10 columns x 2 pixels (pvis + psig)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float v_own = (float)((lane >> 3) + 4 * h) - 3.5f;
@@ -1569,8 +1584,12 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
       d[3] = v_c[h][0]; d[4] = v_c[h][1]; d[5] = v_c[h][2]; d[6] = v_c[h][3];
       d[7] = v_ds[h]; d[8] = v_ds[h] * u_own; d[9] = v_ds[h] * v_own;
     }
-    if (t < 8 * 12) wc.sig[t] = g_b3_sig.v[t];   // (visible to the other warps after the barrier below)
-    if (lane == 0) w.zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < 8 * 12) {                            // (visible to the other warps after the barrier below)
+      const float4 q = g_b3_sig.v[t];
+      wc.sig[0][t] = make_float2(q.x, q.y);
+      wc.sig[1][t] = make_float2(q.z, q.w);
+    }
+    if (lane == 0) w.zero = make_float2(0.f, 0.f);
     __syncwarp();
     if (lane < 20) {
 #pragma unroll
@@ -1580,8 +1599,10 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
         float hi[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) hi[i] = __uint_as_float(__float_as_uint(c[i]) & 0xffffe000u);
-        w.cah[ks * 20 + lane] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        w.cal[ks * 20 + lane] = make_float4(c[0] - hi[0], c[1] - hi[1], c[2] - hi[2], c[3] - hi[3]);
+        w.cah[0][ks * 20 + lane] = make_float2(hi[0], hi[1]);
+        w.cah[1][ks * 20 + lane] = make_float2(hi[2], hi[3]);
+        w.cal[0][ks * 20 + lane] = make_float2(c[0] - hi[0], c[1] - hi[1]);
+        w.cal[1][ks * 20 + lane] = make_float2(c[2] - hi[2], c[3] - hi[3]);
       }
     }
     __syncwarp();   // the scratch rows (parking lot) may be overwritten from here on
@@ -1662,10 +1683,11 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
           pv[h] = vis;
           pv[2 + h] = unc[h] ? -am[h] * v_alpha : 0.f;   // v_sigma
         }
-        w.park[np * B3_PSTRIDE + lane] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+        w.pvis[np * B3_PSTRIDE + lane] = make_float2(pv[0], pv[1]);
+        w.psig[np * B3_PSTRIDE + lane] = make_float2(pv[2], pv[3]);
         if (lane == 0) w.meta[np] = make_float4(xy.x - rcx, xy.y - rcy, q2.w, 0.f);
         if (++np == B3_PEND) {
-          bwd3_flush(w, wc.sig, B3_PEND, a.geom_grad, lane);
+          bwd3_flush(w, wc, B3_PEND, a.geom_grad, lane);
           np = 0;
         }
       }
@@ -1673,7 +1695,7 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
     if (b >= 2 && t < BATCH) s.ids[b & 1][t] = next_id;
   }
   rs::cp_async_wait_all();
-  if (np > 0) bwd3_flush(w, wc.sig, np, a.geom_grad, lane);   // rows >= np hold stale values: their columns are never committed
+  if (np > 0) bwd3_flush(w, wc, np, a.geom_grad, lane);   // rows >= np hold stale values: their columns are never committed
 }
 
 // ------------------------------------------------------------------------------------------------ launch
@@ -1687,7 +1709,7 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   RS_RETURN_LAST_ERROR();
 }
 // per-call options (include/rade_b200.h); the values must match the header's
-constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_SHUFFLE = 0x8;
+constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_MMA = 0x8;
 static inline int bwd_tune(int flags) { return (flags >> 8) & 0xf; }
 
 template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
@@ -1745,7 +1767,7 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
       const int grid = a.C * a.tile_w * a.tile_h;
       // MINB = CTAs per SM the register allocation is capped for: 4 -> 94 registers, 6 -> 80, 7 -> 72 (no spills)
       const int tune = bwd_tune(a.flags);
-      if (!a.abs_grad && !(a.flags & F_BWD_SHUFFLE)) {   // (absgrad sums |per-pixel gradient|: not linear, keeps the shuffle tree)
+      if (!a.abs_grad && (a.flags & F_BWD_MMA)) {   // opt-in (absgrad sums |per-pixel gradient|: not linear, shuffle tree only)
         // RS_RASTER_BWD_TUNE: 0 (default) = 64-Gaussian batches, 4 CTAs/SM; 1 = 128-Gaussian batches, 3 CTAs/SM
 #define RS_LAUNCH_BWD3(BT, MINB)                                                                                    \
   do {                                                                                                              \

@@ -90,6 +90,8 @@ _SIGNATURES = {
     "rs_feature_hidden_fwd": (_i, [_p] + [_i] * 7 + [_p, _p, _i, _p, _p, _p]),
     "rs_feature_branch": (_i, [_p, _i, _i, _i, _p, _p, _i, _p, _i, _i, _f] + [_p] * 6 + [_p]),
     "rs_feature_hidden_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "rs_rade_outputs_fwd": (_i, [_p] * 6 + [_f, _f] + [_i] * 5 + [_p] * 7 + [_p]),
+    "rs_rade_outputs_bwd": (_i, [_p] * 6 + [_f, _f] + [_i] * 5 + [_p] * 12 + [_p]),
     "rs_rade_loss_fwd_bwd": (_i, [_p] * 7 + [_f, _f, _i, _i, _i, _f, _f, _f, _i] + [_p] * 6 + [_p]),
 }
 
@@ -97,7 +99,7 @@ _SIGNATURES = {
 RS_RASTER_CULL_BBOX = 0x1
 RS_RASTER_ONE_PIXEL = 0x2
 RS_RASTER_NO_COLOR_MMA = 0x4
-RS_RASTER_BWD_SHUFFLE = 0x8
+RS_RASTER_BWD_MMA = 0x8
 
 
 def RS_RASTER_BWD_TUNE(x: int) -> int:

@@ -128,8 +128,7 @@ class ShGradExchange:
         self.rank = dist.get_rank(group) if ready else 0
         if self.world > 16:
             raise NotImplementedError("ShGradExchange supports up to 16 ranks (one NVSwitch domain)")
-        self.region_bytes = int(self.lib.rs_sh_region_bytes(self.C, self.N))
-        self.region_stride = (self.region_bytes + 255) // 256 * 256
+        self.region_bytes = int(self.lib.rs_sh_region_bytes(self.C, self.N))   # what THIS rank publishes per step
         self.step = 0
         self._pending = None
         self._out = None
@@ -145,6 +144,10 @@ class ShGradExchange:
             dist.all_gather_object(got, self.C, group=group)
             cams = [int(c) for c in got]
         self.cams = cams
+        # Every rank derives the slot stride (and the inbox allocation) from the LARGEST per-rank camera count, so that
+        # a sender's offset into a peer's inbox and the receiver's own view of it agree when the views of a step do not
+        # divide evenly (shard_views gives ceil and floor shards); a rank still copies only its own region_bytes.
+        self.region_stride = (int(self.lib.rs_sh_region_bytes(max(cams), self.N)) + 255) // 256 * 256
         with torch.cuda.device(self.device):
             if mode in ("p2p", "push"):
                 self._init_p2p()

@@ -138,7 +138,10 @@ int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the
                                         ellipse-vs-rectangle test */
 #define RS_RASTER_ONE_PIXEL 0x2      /* <= 4 channels: one pixel per lane (8x4 block per warp) instead of two (8x8) */
 #define RS_RASTER_NO_COLOR_MMA 0x4   /* >= 20 channels: SIMT colour blend / colour-gradient reduction instead of mma.sync */
-#define RS_RASTER_BWD_SHUFFLE 0x8    /* <= 4 channels backward: shuffle-tree reduction instead of the mma.sync contraction */
+#define RS_RASTER_BWD_MMA 0x8        /* <= 4 channels backward: per-Gaussian reduction as an mma.sync contraction of parked
+                                        (vis, v_sigma) against per-pixel constants instead of the shuffle tree: 27 % fewer
+                                        instructions, but shared-memory-latency bound -- measured 0.96-0.99 ms vs 0.94 ms at
+                                        config 2 (profiles/r02_bwd_mma_ab.txt), so not the default */
 #define RS_RASTER_BWD_TUNE(x) (((x) & 0xf) << 8)   /* backward occupancy / batch variant (0 = default), see rasterize.cu */
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,
@@ -319,6 +322,24 @@ int rs_rade_loss_fwd_bwd(const float* render /* [H,W,D] */, const float* alphas,
                          float fx, float fy, int width, int height, int D, float w_l1, float w_exp, float w_med,
                          int use_depth_normal, float* sums, float* v_render, float* v_alphas, float* v_exp_depth,
                          float* v_med_depth, float* v_normals, void* stream);
+
+/* ---- get_outputs epilogue of the rade-gs model, one camera (replaces the torch glue of
+ * collab_splats/models/rade_gs_model.py:200-271 after the rasterization call): rgb = clamp(render[:3] + (1 - alpha) *
+ * background, 0, 1); depth_im / depth / median_depth / (normals + 1) / 2 with where(alpha > 0, x, max(x)); the two
+ * depth-normal error maps 1 - <normals, depth_double_to_normal(...)[k]> (zero when use_depth_normal == 0).
+ * maxima: 4 x u32 device scratch, zero-filled by the caller.  depth_channel: the "ED" channel of render (3) or -1.
+ * error_maps: [2,H,W].  The backward takes upstream gradients of the outputs (NULL = zero) and writes the gradients of
+ * the five inputs; g_exp_depth / g_med_depth must be zero-filled by the caller. */
+int rs_rade_outputs_fwd(const float* render, const float* alphas, const float* exp_depth, const float* med_depth,
+                        const float* normals, const float* background, float fx, float fy, int width, int height, int D,
+                        int depth_channel, int use_depth_normal, uint32_t* maxima, float* rgb, float* depth,
+                        float* median_depth, float* depth_im, float* normals_out, float* error_maps, void* stream);
+int rs_rade_outputs_bwd(const float* render, const float* alphas, const float* exp_depth, const float* med_depth,
+                        const float* normals, const float* background, float fx, float fy, int width, int height, int D,
+                        int depth_channel, int use_depth_normal, const float* v_rgb, const float* v_depth,
+                        const float* v_median_depth, const float* v_depth_im, const float* v_normals_out,
+                        const float* v_error_maps, const float* v_accumulation, float* g_render, float* g_alphas,
+                        float* g_exp_depth, float* g_med_depth, float* g_normals, void* stream);
 
 #ifdef __cplusplus
 }

@@ -108,8 +108,12 @@ def fully_fused_projection(
     far_plane: float = 1e10,
     radius_clip: float = 0.0,
     calc_compensations: bool = False,
+    radii_override: Optional[Tensor] = None,
 ):
     """Restates gsplat ``fully_fused_projection`` (packed=False, pinhole) + RaDe terms.
+
+    ``radii_override`` (test aid): take the integer radii -- and with them the culling decision -- from another run
+    instead of deriving them here, so that an fp64 evaluation follows the discrete decisions of the fp32 one.
 
     Follows SURVEY.md rows a5 / Appendix A1-A5; call site rade_gs_model.py:373-389.
     Returns the 8-tuple the reference unpacks at rade_gs_model.py:392-394:
@@ -213,6 +217,9 @@ def fully_fused_projection(
     valid = valid & ~((rx <= radius_clip) & (ry <= radius_clip))
     valid = valid & ~((m2x + rx <= 0) | (m2x - rx >= width) | (m2y + ry <= 0) | (m2y - ry >= height))
     valid = valid & torch.isfinite(rx) & torch.isfinite(ry)
+    if radii_override is not None:
+        valid = (radii_override > 0).all(dim=-1)
+        rx, ry = radii_override[..., 0].to(dt), radii_override[..., 1].to(dt)
 
     # ---- A5 RaDe ray-space plane + normal (clamped u,v)
     l2 = (u * u + v * v) + 1.0
@@ -549,10 +556,16 @@ def rasterization(
     sh_degree: Optional[int] = None, tile_size: int = 16, backgrounds: Optional[Tensor] = None,
     render_mode: str = "RGB", rasterize_mode: str = "classic", return_depth_normal: bool = False,
     return_aux: bool = False, tile_window: Optional[Tuple[int, int, int, int]] = None,
-    compositor: str = "torch", threads: Optional[int] = None,
+    compositor: str = "torch", threads: Optional[int] = None, discrete_from: Optional[Dict] = None,
+    fragile_scale: float = 1.0,
 ):
     """Restates ``gsplat.rendering.rasterization`` for the options the reference uses
     (call site rade_gs_model.py:439-465): packed=False, pinhole, 3DGS.
+
+    ``discrete_from`` (test aid): the ``meta`` of another run of the same scene; its integer artefacts (radii, tile
+    lists, sort order, offsets) are used instead of recomputing them.  The render is a discontinuous function of the
+    inputs through those integers (a radius that rounds the other way adds or removes tiles), so an fp64 evaluation
+    that is to serve as the ground truth of an fp32 one has to follow the fp32 run's discrete decisions.
 
     ``compositor="c"`` runs the per-tile compositing stage (forward and backward) through the C restatement
     (oracle/raster_oracle.c, ``threads`` host threads) instead of the PyTorch one; everything else is unchanged."""
@@ -561,7 +574,8 @@ def rasterization(
     C, N = viewmats.shape[0], means.shape[0]
     radii, means2d, depths, conics, comps, ray_ts, ray_planes, normals = fully_fused_projection(
         means, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, near_plane=near_plane,
-        far_plane=far_plane, radius_clip=radius_clip, calc_compensations=(rasterize_mode == "antialiased"))
+        far_plane=far_plane, radius_clip=radius_clip, calc_compensations=(rasterize_mode == "antialiased"),
+        radii_override=None if discrete_from is None else discrete_from["radii"])
     opac = opacities[None, :].expand(C, N)
     if comps is not None:
         opac = opac * comps
@@ -583,13 +597,17 @@ def rasterization(
             backgrounds = torch.zeros(C, 1, dtype=backgrounds.dtype)
     TW = math.ceil(width / tile_size)
     TH = math.ceil(height / tile_size)
-    tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, TW, TH)
-    isect_offsets = isect_offset_encode(isect_ids, C, TW, TH)
+    if discrete_from is None:
+        tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(means2d, radii, depths, tile_size, TW, TH)
+        isect_offsets = isect_offset_encode(isect_ids, C, TW, TH)
+    else:
+        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = (
+            discrete_from[k] for k in ("tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"))
     if compositor == "c":
         from . import raster_oracle as _RO
         res = _RO.rasterize_to_pixels(means2d, conics, cols, opac, ray_ts, ray_planes, normals, Ks, width, height,
                                       tile_size, isect_offsets, flatten_ids, backgrounds=backgrounds,
-                                      return_aux=True, threads=threads)
+                                      return_aux=True, threads=threads, fragile_scale=fragile_scale)
     else:
         assert compositor == "torch", compositor
         res = rasterize_to_pixels(means2d, conics, cols, opac, ray_ts, ray_planes, normals, Ks, width, height,
@@ -640,3 +658,29 @@ def depth_normal_loss(Ks_c: Tensor, width: int, height: int, exp_depth: Tensor, 
     err = 1.0 - (rendered_normals[None] * n_d).sum(dim=-1)                       # [2,H,W]
     loss = lam * ((1.0 - depth_ratio) * err[0].mean() + depth_ratio * err[1].mean())
     return loss, err
+
+
+def get_outputs_glue(Ks_c: Tensor, width: int, height: int, render: Tensor, alpha: Tensor, expected_depths: Tensor,
+                     median_depths: Tensor, expected_normals: Tensor, background: Tensor, render_mode: str = "RGB+ED",
+                     use_depth_normal: bool = True) -> Dict[str, Optional[Tensor]]:
+    """Restates the part of ``RadegsModel.get_outputs`` that follows the rasterization call
+    (collab_splats/models/rade_gs_model.py:200-271) for one camera: render [H,W,D], alpha /
+    depths [H,W,1], expected_normals [H,W,3], background [3] -> the reference's output dict.  Pinned to the
+    reference's own lines by tests/golden/rade_outputs.npz (tests/golden/make_outputs_golden.py)."""
+    if use_depth_normal:
+        n_d = depth_double_to_normal(Ks_c, width, height, expected_depths[..., 0], median_depths[..., 0])  # [2,H,W,3]
+        err = 1.0 - (expected_normals[None] * n_d).sum(dim=-1)                                            # [2,H,W]
+    else:
+        err = torch.zeros(2, height, width, dtype=render.dtype, device=render.device)
+    normals = (expected_normals + 1) / 2
+    rgb = torch.clamp(render[..., :3] + (1 - alpha) * background, 0.0, 1.0)
+    hit = alpha > 0
+    depth_im = None
+    if render_mode == "RGB+ED":
+        d = render[..., 3:4]
+        depth_im = torch.where(hit, d, d.detach().max())
+    return {"rgb": rgb, "depth": torch.where(hit, expected_depths, expected_depths.detach().max()),
+            "median_depth": torch.where(hit, median_depths, median_depths.detach().max()), "depth_im": depth_im,
+            "accumulation": alpha, "normals": torch.where(hit, normals, normals.detach().max()),
+            "depth_normal_error_map": err[0][..., None], "middepth_normal_error_map": err[1][..., None],
+            "background": background}

@@ -42,7 +42,7 @@ def load():
         _lib = C.CDLL(str(build()))
         p, i, ll = C.c_void_p, C.c_int, C.c_longlong
         for sfx in ("_f32", "_f64"):
-            getattr(_lib, "ro_rasterize_fwd" + sfx).argtypes = [i] * 7 + [p] * 11 + [ll] + [p] * 9 + [i]
+            getattr(_lib, "ro_rasterize_fwd" + sfx).argtypes = [i] * 7 + [p] * 11 + [ll] + [p] * 9 + [C.c_double, i]
             getattr(_lib, "ro_rasterize_fwd" + sfx).restype = i
             getattr(_lib, "ro_rasterize_bwd" + sfx).argtypes = [i] * 7 + [p] * 11 + [ll] + [p] * 15 + [i]
             getattr(_lib, "ro_rasterize_bwd" + sfx).restype = i
@@ -56,7 +56,7 @@ def _ptr(t: Optional[Tensor]):
 class _CRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opac, ray_ts, ray_planes, normals, backgrounds, Ks, width, height,
-                offsets, flatten_ids, threads, want_fragile):
+                offsets, flatten_ids, threads, want_fragile, fragile_scale=1.0):
         lib = load()
         dt = means2d.dtype
         assert dt in (torch.float32, torch.float64)
@@ -81,7 +81,7 @@ class _CRasterize(torch.autograd.Function):
         rc = getattr(lib, "ro_rasterize_fwd" + sfx)(
             Cn, N, D, width, height, tw, th, *[_ptr(t) for t in ins], _ptr(bg), _ptr(offs), _ptr(flat), M,
             _ptr(out_c), _ptr(out_a), _ptr(out_de), _ptr(out_dm), _ptr(out_n), _ptr(last), _ptr(med), _ptr(frag),
-            _ptr(counters), int(threads))
+            _ptr(counters), float(fragile_scale), int(threads))
         assert rc == 0
         ctx.save_for_backward(*ins, bg, offs, flat, last, med)
         ctx.cfg = (Cn, N, D, width, height, tw, th, M, sfx, int(threads), backgrounds is not None)
@@ -111,22 +111,26 @@ class _CRasterize(torch.autograd.Function):
             _ptr(med), _ptr(v_c), _ptr(v_a), _ptr(v_de), _ptr(v_dm), _ptr(v_n), *[_ptr(g) for g in grads], _ptr(g_bg),
             threads)
         assert rc == 0
-        return (*grads, g_bg, None, None, None, None, None, None, None)
+        return (*grads, g_bg, None, None, None, None, None, None, None, None)
 
 
 def rasterize_to_pixels(means2d: Tensor, conics: Tensor, colors: Tensor, opacities: Tensor, ray_ts: Tensor,
                         ray_planes: Tensor, normals: Tensor, Ks: Tensor, width: int, height: int, tile_size: int,
                         isect_offsets: Tensor, flatten_ids: Tensor, backgrounds: Optional[Tensor] = None,
-                        return_aux: bool = False, tile_window=None, threads: Optional[int] = None):
+                        return_aux: bool = False, tile_window=None, threads: Optional[int] = None,
+                        fragile_scale: float = 1.0):
     """Same contract as ``rade_oracle.rasterize_to_pixels`` (colours may be [N,D] or [C,N,D]; ``tile_window`` is not
-    supported -- the point of the C oracle is that complete views are affordable)."""
+    supported -- the point of the C oracle is that complete views are affordable).  ``fragile_scale`` widens the margins
+    of the ``fragile`` mask (1 = the margins of the PyTorch oracle, right for two fp32 implementations of the same
+    arithmetic; an fp32-against-fp64 comparison needs ~10: a transmittance that is a product of hundreds of fp32
+    factors is ~1e-5 off, which is the width of the median-crossing margin)."""
     assert tile_size == 16 and tile_window is None
     Cn, N = opacities.shape
     if colors.dim() == 2:
         colors = colors[None].expand(Cn, N, colors.shape[-1])
     out = _CRasterize.apply(means2d, conics, colors, opacities, ray_ts, ray_planes, normals, backgrounds, Ks,
                             int(width), int(height), isect_offsets, flatten_ids, int(threads or THREADS),
-                            bool(return_aux))
+                            bool(return_aux), float(fragile_scale))
     res = tuple(out[:5])
     if return_aux:
         aux = dict(last_ids=out[5], median_ids=out[6], fragile=out[7].bool(), n_tested=int(out[8][0]),

@@ -20,6 +20,7 @@ typedef struct {
   const REAL *v_colors, *v_alphas, *v_dexp, *v_dmed, *v_normals;
   REAL *g_means2d, *g_conics, *g_colors, *g_opac, *g_ray_ts, *g_ray_planes, *g_normals, *g_backgrounds;
   int backward;
+  double margin; /* scale of the 'fragile' margins (1 = the margins of rade_oracle.py) */
   int next_tile; /* work queue (atomic) */
 } FN(Job);
 
@@ -75,10 +76,10 @@ static void FN(tile_fwd)(const FN(Job) * j, int tid, int64_t* n_tested, int64_t*
         const REAL a_raw = j->opac[g] * EXP(-sigma);
         const REAL alpha = a_raw < (REAL)RO_ALPHA_MAX ? a_raw : (REAL)RO_ALPHA_MAX;
         ++*n_tested;
-        if (sigma >= 0 && FABS(alpha - (REAL)RO_ALPHA_MIN) < (REAL)(2e-4 * RO_ALPHA_MIN)) frag = 1;
+        if (sigma >= 0 && FABS(alpha - (REAL)RO_ALPHA_MIN) < (REAL)(2e-4 * RO_ALPHA_MIN * j->margin)) frag = 1;
         if (!(sigma >= 0 && alpha >= (REAL)RO_ALPHA_MIN)) continue;
         const REAL nT = T * ((REAL)1 - alpha);
-        if (FABS(nT - (REAL)RO_T_STOP) < (REAL)(2e-4 * RO_T_STOP) || FABS(nT - (REAL)0.5) < (REAL)1e-5) frag = 1;
+        if (FABS(nT - (REAL)RO_T_STOP) < (REAL)(2e-4 * RO_T_STOP * j->margin) || FABS(nT - (REAL)0.5) < (REAL)(1e-5 * j->margin)) frag = 1;
         if (!(nT > (REAL)RO_T_STOP)) break; /* the pixel is saturated: this Gaussian is not blended */
         const REAL vis = alpha * T;
         const REAL t = j->ray_ts[g] + j->ray_planes[2 * (size_t)g] * dx + j->ray_planes[2 * (size_t)g + 1] * dy;
@@ -288,7 +289,8 @@ int FN(ro_rasterize_fwd)(int C, int N, int D, int W, int H, int tile_w, int tile
                          const REAL* ray_planes, const REAL* normals, const REAL* Ks, const REAL* backgrounds,
                          const int32_t* offsets, const int32_t* flatten_ids, int64_t M, REAL* out_colors,
                          REAL* out_alphas, REAL* out_dexp, REAL* out_dmed, REAL* out_normals, int32_t* last_ids,
-                         int32_t* median_ids, uint8_t* fragile, int64_t* counters, int threads) {
+                         int32_t* median_ids, uint8_t* fragile, int64_t* counters, double fragile_margin_scale,
+                         int threads) {
   FN(Job) j;
   memset(&j, 0, sizeof(j));
   j.C = C; j.N = N; j.D = D; j.W = W; j.H = H; j.tile_w = tile_w; j.tile_h = tile_h;
@@ -298,6 +300,7 @@ int FN(ro_rasterize_fwd)(int C, int N, int D, int W, int H, int tile_w, int tile
   j.out_colors = out_colors; j.out_alphas = out_alphas; j.out_dexp = out_dexp; j.out_dmed = out_dmed;
   j.out_normals = out_normals; j.last_ids = last_ids; j.median_ids = median_ids; j.fragile = fragile;
   j.counters = counters;
+  j.margin = fragile_margin_scale > 0 ? fragile_margin_scale : 1.0;
   j.backward = 0;
   return FN(run)(&j, threads);
 }

@@ -26,10 +26,10 @@ def step():
     return [t.detach() for t in o[:5]], [t.grad.clone() for t in p]
 ref = None
 from gsplat.cuda import _wrapper as W
-VARIANTS = (("1px", be.RS_RASTER_ONE_PIXEL), ("2px shuffle bwd", be.RS_RASTER_BWD_SHUFFLE),
-            ("2px mma bwd (default)", 0), ("2px mma bwd 128/3", be.RS_RASTER_BWD_TUNE(1)),
-            ("2px shuffle bwd", be.RS_RASTER_BWD_SHUFFLE), ("2px mma bwd (default)", 0),
-            ("2px mma bwd 128/3", be.RS_RASTER_BWD_TUNE(1)))
+MMA = be.RS_RASTER_BWD_MMA
+VARIANTS = (("1px", be.RS_RASTER_ONE_PIXEL), ("2px shuffle bwd (default)", 0), ("2px mma bwd", MMA),
+            ("2px mma bwd 128/3", MMA | be.RS_RASTER_BWD_TUNE(1)), ("2px shuffle bwd (default)", 0), ("2px mma bwd", MMA),
+            ("2px mma bwd 128/3", MMA | be.RS_RASTER_BWD_TUNE(1)))
 for name, flags in VARIANTS:
     W.RASTER_FLAGS = flags
     for _ in range(3): o, g = step()

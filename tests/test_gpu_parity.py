@@ -255,13 +255,13 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
 
 @pytest.fixture
 def raster_variant(request):
-    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane, backward
-    reduced on the tensor cores, 2: 8x8 with the shuffle-tree backward; +10: with the bbox footprint test instead of the
-    exact ellipse-vs-rectangle one) through the per-call flags for the duration of a test."""
+    """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane -- the
+    default --, 2: 8x8 with the backward's per-Gaussian reduction on the tensor cores; +10: with the bbox footprint test
+    instead of the exact ellipse-vs-rectangle one) through the per-call flags for the duration of a test."""
     from radegs_b200 import backend as be
     from gsplat.cuda import _wrapper as W
     v = request.param % 10
-    flags = {0: be.RS_RASTER_ONE_PIXEL, 1: 0, 2: be.RS_RASTER_BWD_SHUFFLE}[v]
+    flags = {0: be.RS_RASTER_ONE_PIXEL, 1: 0, 2: be.RS_RASTER_BWD_MMA}[v]
     if request.param >= 10:
         flags |= be.RS_RASTER_CULL_BBOX
     old = W.RASTER_FLAGS
@@ -551,6 +551,75 @@ def test_full_size_window_matches_oracle(cuda_dev, cfg_id, win):
         ok, msg = grad_close_report("v_" + nm, a.grad, b.grad, rel=3e-3)
         assert ok, msg
         assert float(b.grad.abs().max()) > 0
+
+
+FULL_VIEW_CASES = {
+    # BASELINE config -> (views rendered, what it adds).  Config 4 is a 2-view slice of its 8-view batch (camera bits
+    # in the sort keys at 3 M Gaussians), config 5 is forward only (the meshing sweep renders under no_grad).
+    2: dict(views=1, sh=3, backward=True), 3: dict(views=1, sh=None, backward=True),
+    4: dict(views=2, sh=3, backward=True), 5: dict(views=1, sh=3, backward=False),
+}
+
+
+@pytest.mark.parametrize("cfg_id", [2, 3, 4, 5])
+def test_full_view_matches_c_oracle(cuda_dev, cfg_id):
+    """Every BASELINE GPU config at FULL size against the oracle on the COMPLETE view(s): the oracle's projection, SH,
+    intersection and sort run in PyTorch on the CPU, its compositing forward/backward in C (oracle/raster_oracle.c,
+    pinned to the PyTorch restatement by tests/test_c_oracle.py).  Integer artefacts bit for bit; every pixel of every
+    output within max-abs 1e-4 + rel 1e-3 outside the oracle's fragile pixels; the gradients of all five inputs, for a
+    random cotangent over the whole view, per element against the fp64 oracle and against the fp32 oracle's own error
+    (tests/util.py:grad_parity_report)."""
+    from gsplat.rendering import rasterization
+    from tests.util import grad_parity_report
+    case = FULL_VIEW_CASES[cfg_id]
+    cfg = scenes.BASELINE_CONFIGS[cfg_id]
+    gs, vm, Ks = scenes.make_scene(cfg, n_views=case["views"])
+    sh = case["sh"]
+    params = scenes.activate(gs, sh)
+    W, H, C = cfg.width, cfg.height, case["views"]
+    kw = dict(sh_degree=sh, render_mode="RGB+ED", rasterize_mode="antialiased", return_depth_normal=True)
+    cpu = [t.detach().clone().requires_grad_(case["backward"]) for t in params]
+    ref = O.rasterization(*cpu, vm, Ks, W, H, return_aux=True, compositor="c", **kw)
+    gpu = _gpu(params, cuda_dev, grad=case["backward"])
+    with torch.set_grad_enabled(case["backward"]):
+        got = rasterization(*gpu, vm.to(cuda_dev), Ks.to(cuda_dev), W, H, packed=False, **kw)
+    meta, rmeta = got[5], ref[5]
+    assert rmeta["isect_ids"].numel() > 2_000_000
+    if C > 1:
+        assert int(rmeta["isect_ids"].max() >> 45) >= 1, "camera bits are not exercised"
+    for key in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):
+        assert torch.equal(meta[key].cpu(), rmeta[key]), f"meta[{key}] differs at full size"
+    keep = ~rmeta["fragile"]
+    assert float(ref[1].detach().mean()) > 0.5 and int((~keep).sum()) < keep.numel() // 20
+    for i, nm in enumerate(["render", "alpha", "expected_depths", "median_depths", "expected_normals"]):
+        ok, msg = close_report(nm, got[i], ref[i], mask=keep)
+        assert ok, msg
+    if not case["backward"]:
+        return
+    # The gradients are compared with an fp64 evaluation, which only makes sense on pixels whose discrete decisions
+    # (alpha >= 1/255, T <= 1e-4, median crossing) fp32 and fp64 take alike: wider margins than for the images.
+    with torch.no_grad():
+        wide = O.rasterization(*[t.detach() for t in cpu], vm, Ks, W, H, return_aux=True, compositor="c",
+                               discrete_from=rmeta, fragile_scale=10.0, **kw)[5]["fragile"]
+    keep64 = keep & ~wide
+    assert int((~keep64).sum()) < keep64.numel() // 5
+    g = torch.Generator().manual_seed(4)
+    ws = [torch.randn(t.shape, generator=g) * keep64[..., None] for t in ref[:5]]
+    sum((t * w).sum() for t, w in zip(ref[:5], ws)).backward()
+    sum((t * w.to(cuda_dev)).sum() for t, w in zip(got[:5], ws)).backward()
+    d64 = [t.detach().double().clone().requires_grad_(True) for t in params]
+    # fp64 ground truth along the fp32 run's discrete decisions (radii, tile lists): the render is discontinuous in them
+    r64 = O.rasterization(*d64, vm.double(), Ks.double(), W, H, compositor="c", discrete_from=rmeta, **kw)
+    sum((t * w.double()).sum() for t, w in zip(r64[:5], ws)).backward()
+    report = []
+    all_ok = True
+    for nm, a, b32, b64 in zip(("means", "quats", "scales", "opacities", "colors"), gpu, cpu, d64):
+        ok, msg = grad_parity_report("v_" + nm, a.grad, b64.grad, b32.grad, outlier_frac=2e-6)
+        report.append(msg)
+        all_ok &= ok
+        assert float(b64.grad.abs().max()) > 0
+    print("\n".join(report))
+    assert all_ok, "\n".join(report)
 
 
 # ------------------------------------------------------------------------------------------------ fused loss (8f row f1)

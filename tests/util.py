@@ -66,3 +66,50 @@ def grad_close_report(name, got, ref, rel=2e-3, floor=1e-6):
             t = tuple(i.tolist())
             msg += f"\n    at {t}: got {got[t].item():.6e} ref {ref[t].item():.6e}"
     return n_bad == 0, msg
+
+
+def grad_parity_report(name, got, ref64, ref32=None, atol_rel=1e-4, rtol=RTOL, factor=4.0, floor_rel=2e-6,
+                       outlier_frac=0.0, outlier_atol_rel=2e-3):
+    """Gradient parity in the north star's form, per element, against the fp64 oracle:
+
+        |got - ref64| <= atol_rel * s + rtol * |ref64|        with s = max |ref64| (the tensor's own unit)
+
+    i.e. "max-abs 1e-4, rel 1e-3" with the absolute part expressed in units of the tensor's largest gradient (a
+    gradient has no natural unit of its own: it scales with the loss).  When the fp32 oracle's gradient is given as
+    well, the GPU's error must also stay within what fp32 arithmetic itself does to this sum:
+
+        rms(got - ref64) <= factor * rms(ref32 - ref64) + floor_rel * s,   max likewise with 2 * factor
+
+    (atomics reorder the sums and the kernels use ex2.approx / rcp.approx, so a small multiple, not equality).
+    ``outlier_frac`` > 0 tolerates that fraction of elements outside the per-element bound as long as they stay
+    within ``outlier_atol_rel * s``: at a million Gaussians a handful of pixels take a discrete decision differently in
+    fp32 and fp64 despite the margins, which moves single Gaussians' gradients by ~1e-3 of their size.
+    The message also carries the worst relative error over the elements with |ref64| > 1e-3 * s."""
+    if got is None:
+        got = torch.zeros_like(ref64)
+    got = got.detach().double().cpu()
+    ref64 = ref64.detach().double().cpu()
+    assert got.shape == ref64.shape, (name, got.shape, ref64.shape)
+    s = ref64.abs().max().item()
+    err = (got - ref64).abs()
+    bad = err > atol_rel * s + rtol * ref64.abs()
+    n_bad = int(bad.sum())
+    big = ref64.abs() > 1e-3 * s
+    worst_rel = (err[big] / ref64.abs()[big]).max().item() if bool(big.any()) else 0.0
+    msg = (f"{name}: scale={s:.3e} max_abs_err={err.max().item():.3e} ({err.max().item() / (s + 1e-300):.2e} of scale) "
+           f"worst_rel(|ref|>1e-3 s)={worst_rel:.2e} violations={n_bad}/{err.numel()}")
+    ok = n_bad <= int(outlier_frac * err.numel()) and (n_bad == 0 or err.max().item() <= outlier_atol_rel * s)
+    if ref32 is not None:
+        e32 = (ref32.detach().double().cpu() - ref64).abs()
+        rms_g, rms_o = err.pow(2).mean().sqrt().item(), e32.pow(2).mean().sqrt().item()
+        max_g, max_o = err.max().item(), e32.max().item()
+        msg += (f" | rms err gpu {rms_g:.3e} vs fp32 oracle {rms_o:.3e}; max err gpu {max_g:.3e} vs fp32 oracle "
+                f"{max_o:.3e}")
+        if rms_g > factor * rms_o + floor_rel * s or max_g > 2 * factor * max_o + 10 * floor_rel * s:
+            ok = False
+            msg += "  <-- GPU error exceeds the fp32 oracle's own error budget"
+    if n_bad:
+        for i in torch.nonzero(bad)[:5]:
+            t = tuple(i.tolist())
+            msg += f"\n    at {t}: got {got[t].item():.6e} ref64 {ref64[t].item():.6e}"
+    return ok, msg
