@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(OB) outputs_fwd_kernel(const OutArgs a) {
   const float* rc = a.render + p * a.D;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    const float raw = __ldg(rc + k) + (1.f - alpha) * __ldg(a.background + k);
+    // (separately rounded product and sum, as the reference's two torch kernels: no FMA contraction)
+    const float raw = __fadd_rn(__ldg(rc + k), __fmul_rn(1.f - alpha, __ldg(a.background + k)));
     a.rgb[p * 3 + k] = fminf(fmaxf(raw, 0.f), 1.f);
   }
   if (a.depth_im) a.depth_im[p] = hit ? __ldg(rc + a.depth_ch) : key2f(a.maxima[0]);
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(OB) outputs_bwd_kernel(const OutArgs a) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float bg = __ldg(a.background + k);
-    const float raw = __ldg(rc + k) + (1.f - alpha) * bg;
+    const float raw = __fadd_rn(__ldg(rc + k), __fmul_rn(1.f - alpha, bg));
     float g = a.v_rgb ? __ldg(a.v_rgb + p * 3 + k) : 0.f;
     if (!(raw >= 0.f && raw <= 1.f)) g = 0.f;   // clamp passes the gradient only inside [0,1]
     gr[k] = g;

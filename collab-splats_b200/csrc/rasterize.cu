@@ -639,19 +639,21 @@ __device__ __forceinline__ float sigma_col(float adx2, float bdx, float c, float
 // count of the (issue-bound) alpha test; 4 warps (128 threads) per tile, 128-Gaussian batches.
 constexpr int RT2 = 128;
 
-template <int DP, int BATCH, bool STATS>
-__global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a) {
+template <int DP, int BATCH, bool STATS, int NW>
+__global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArgs a) {
+  constexpr int NT = NW * 32, SUB = 4 / NW;   // NW warps per CTA: a CTA covers NW of the tile's four 8x8 blocks
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int tile_id = blockIdx.x;
+  const int tile_id = blockIdx.x / SUB;
+  const int qd = (blockIdx.x - tile_id * SUB) * NW + warp;   // which 8x8 block of the tile this warp owns
   const int tiles_per_cam = a.tile_w * a.tile_h;
   const int cam = tile_id / tiles_per_cam;
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
   const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
-  const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
+  const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const int pyi[2] = {y0 + (lane >> 3), y0 + (lane >> 3) + 4};
   const bool inside[2] = {pxi < a.W && pyi[0] < a.H, pxi < a.W && pyi[1] < a.H};
@@ -671,23 +673,23 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
 
   const int nb = (end - start + BATCH - 1) / BATCH;
   if (nb > 0) {
-    for (int i = t; i < BATCH; i += RT2) { const int g = start + i; s.ids[0][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+    for (int i = t; i < BATCH; i += NT) { const int g = start + i; s.ids[0][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
     __syncthreads();
-    issue_gather<DP, BATCH, RT2>(s, 0, min(BATCH, end - start), a, t);
+    issue_gather<DP, BATCH, NT>(s, 0, min(BATCH, end - start), a, t);
     if (nb > 1)
-      for (int i = t; i < BATCH; i += RT2) { const int g = start + BATCH + i; s.ids[1][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+      for (int i = t; i < BATCH; i += NT) { const int g = start + BATCH + i; s.ids[1][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
   }
   bool warp_done = !__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f);
   for (int b = 0; b < nb; ++b) {
     rs::cp_async_wait_all();
     if (__syncthreads_count(T[0] != 0.f || T[1] != 0.f) == 0) break;
-    int next_id[BATCH / RT2];
+    int next_id[BATCH / NT];
     if (b + 1 < nb) {
-      issue_gather<DP, BATCH, RT2>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
+      issue_gather<DP, BATCH, NT>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
       if (b + 2 < nb) {
 #pragma unroll
-        for (int r = 0; r < BATCH / RT2; ++r) {
-          const int g = start + (b + 2) * BATCH + r * RT2 + t;
+        for (int r = 0; r < BATCH / NT; ++r) {
+          const int g = start + (b + 2) * BATCH + r * NT + t;
           next_id[r] = g < end ? __ldg(a.flatten_ids + g) : 0;
         }
       }
@@ -775,7 +777,7 @@ __global__ void __launch_bounds__(RT2) rasterize_fwd2_kernel(const RasterArgs a)
     }
     if (b + 2 < nb) {
 #pragma unroll
-      for (int r = 0; r < BATCH / RT2; ++r) s.ids[b & 1][r * RT2 + t] = next_id[r];
+      for (int r = 0; r < BATCH / NT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
     }
   }
   rs::cp_async_wait_all();
@@ -1148,21 +1150,23 @@ __global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const
 // x-dependent terms and -- the point of the variant -- ONE 16-value warp reduction and ONE 64-byte RED per
 // (warp, Gaussian): their contributions are summed in registers first.  Because dx is common to the two pixels
 // the record's moments factor as dx * (sum over the two pixels), which removes most per-pixel multiplies.
-template <int BATCH, bool ABSGRAD, int MINB>
-__global__ void __launch_bounds__(RT2, MINB) rasterize_bwd2_kernel(const RasterArgs a) {
+template <int BATCH, bool ABSGRAD, int MINB, int NW>
+__global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kernel(const RasterArgs a) {
   constexpr int DP = 4;
-  static_assert(BATCH == RT2, "one id per thread");
+  constexpr int NT = NW * 32, SUB = 4 / NW, IPT = BATCH / NT;   // NW warps per CTA; IPT ids per thread and batch
+  static_assert(BATCH % NT == 0, "whole ids per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int tile_id = blockIdx.x;
+  const int tile_id = blockIdx.x / SUB;
+  const int qd = (blockIdx.x - tile_id * SUB) * NW + warp;   // which 8x8 block of the tile this warp owns
   const int tiles_per_cam = a.tile_w * a.tile_h;
   const int cam = tile_id / tiles_per_cam;
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
   const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
-  const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
+  const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const float px = pxi + 0.5f;
   const float rcx = x0 + 4.0f, rcy = y0 + 4.0f;
@@ -1239,23 +1243,33 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd2_kernel(const RasterA
   __syncthreads();
   int blk_last = start - 1;
 #pragma unroll
-  for (int w = 0; w < RT2 / 32; ++w) blk_last = max(blk_last, s.red[w]);
+  for (int w = 0; w < NW; ++w) blk_last = max(blk_last, s.red[w]);
   const int nb = blk_last >= start ? (blk_last - start) / BATCH + 1 : 0;
 
   if (nb > 0) {
     const int bl = nb - 1;
-    { const int i = start + bl * BATCH + t; s.ids[bl & 1][t] = i < end ? __ldg(a.flatten_ids + i) : 0; }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+      const int i = start + bl * BATCH + r * NT + t;
+      s.ids[bl & 1][r * NT + t] = i < end ? __ldg(a.flatten_ids + i) : 0;
+    }
     __syncthreads();
-    issue_gather<DP, BATCH, RT2>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
-    if (bl >= 1) s.ids[(bl - 1) & 1][t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + t);
+    issue_gather<DP, BATCH, NT>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
+    if (bl >= 1) {
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) s.ids[(bl - 1) & 1][r * NT + t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + r * NT + t);
+    }
   }
   for (int b = nb - 1; b >= 0; --b) {
     rs::cp_async_wait_all();
     __syncthreads();
-    int next_id = 0;
+    int next_id[IPT];
     if (b >= 1) {
-      issue_gather<DP, BATCH, RT2>(s, (b - 1) & 1, BATCH, a, t);
-      if (b >= 2) next_id = __ldg(a.flatten_ids + start + (b - 2) * BATCH + t);
+      issue_gather<DP, BATCH, NT>(s, (b - 1) & 1, BATCH, a, t);
+      if (b >= 2) {
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) next_id[r] = __ldg(a.flatten_ids + start + (b - 2) * BATCH + r * NT + t);
+      }
     }
     const int buf = b & 1;
     const int base_idx = start + b * BATCH;
@@ -1360,7 +1374,10 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd2_kernel(const RasterA
         }
       }
     }
-    if (b >= 2) s.ids[b & 1][t] = next_id;
+    if (b >= 2) {
+#pragma unroll
+      for (int r = 0; r < IPT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
+    }
   }
   rs::cp_async_wait_all();
 }
@@ -1729,9 +1746,11 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
   if constexpr (DP == 4) {
     if (!(a.flags & F_ONE_PIXEL)) {
       constexpr int B2 = 128;
-      const size_t smem = sizeof(Smem<DP, B2>);
-      if (a.stats) rasterize_fwd2_kernel<DP, B2, true><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);  // counting only
-      else rasterize_fwd2_kernel<DP, B2, false><<<a.C * a.tile_w * a.tile_h, RT2, smem, st>>>(a);
+      const int tiles = a.C * a.tile_w * a.tile_h;
+      // (CTAs of 2 or 1 warps -- half / quarter tiles, no or less barrier coupling -- were measured slower: every CTA
+      // gathers the whole tile list, profiles/r02_warps_per_cta_ab.txt)
+      if (a.stats) rasterize_fwd2_kernel<DP, B2, true, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);  // counting only
+      else rasterize_fwd2_kernel<DP, B2, false, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
     if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
@@ -1782,10 +1801,10 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
 #undef RS_LAUNCH_BWD3
         RS_RETURN_LAST_ERROR();
       }
-      if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4><<<grid, RT2, smem, st>>>(a);
-      else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7><<<grid, RT2, smem, st>>>(a);
-      else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6><<<grid, RT2, smem, st>>>(a);
-      else rasterize_bwd2_kernel<B2, false, 4><<<grid, RT2, smem, st>>>(a);
+      if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4, 4><<<grid, RT2, smem, st>>>(a);
+      else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7, 4><<<grid, RT2, smem, st>>>(a);
+      else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6, 4><<<grid, RT2, smem, st>>>(a);
+      else rasterize_bwd2_kernel<B2, false, 4, 4><<<grid, RT2, smem, st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
   }

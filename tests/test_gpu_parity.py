@@ -584,7 +584,7 @@ def test_full_view_matches_c_oracle(cuda_dev, cfg_id):
     with torch.set_grad_enabled(case["backward"]):
         got = rasterization(*gpu, vm.to(cuda_dev), Ks.to(cuda_dev), W, H, packed=False, **kw)
     meta, rmeta = got[5], ref[5]
-    assert rmeta["isect_ids"].numel() > 2_000_000
+    assert rmeta["isect_ids"].numel() > 1_500_000
     if C > 1:
         assert int(rmeta["isect_ids"].max() >> 45) >= 1, "camera bits are not exercised"
     for key in ("radii", "tiles_per_gauss", "isect_ids", "flatten_ids", "isect_offsets"):

@@ -90,7 +90,7 @@ def test_outputs_kernel_backward_matches_oracle_autograd(cuda_dev, mode, use_dn)
         w = torch.randn(ref[k].shape, generator=gen)
         lr = lr + (ref[k] * w).sum()
         lg = lg + (got[k] * w.to(cuda_dev)).sum()
-        torch.testing.assert_close(got[k].detach().cpu(), ref[k].detach(), atol=1e-6, rtol=1e-6)
+        torch.testing.assert_close(got[k].detach().cpu(), ref[k].detach(), atol=1e-5 if "error_map" in k else 0.0, rtol=0)
     lr.backward()
     lg.backward()
     for nm, a, b in zip(("render", "alpha", "expected_depths", "median_depths", "normals"), gpu, cpu):
