@@ -260,6 +260,24 @@ class Workload:
         from radegs_b200.multiview import ShGradExchange
         self.exchange, self.exchange_mode = None, mode
         self.collectives_on = True
+        self.peer_ar = None
+        if getattr(self, "small_allreduce", "peer") == "peer" and dist.get_world_size() in (2, 4, 8):
+            # the 11 floats per Gaussian that are not SH coefficients: two-shot all-reduce kernel over peer memory
+            from radegs_b200.multiview import PeerAllReduce
+            n_small = sum(v.numel() for k, v in self.params.items() if k != "sh_coeffs")
+            try:
+                self.peer_ar = PeerAllReduce(n_small, self.device)
+                self.ar_stream = torch.cuda.Stream(self.device)
+            except Exception as e:  # noqa: BLE001
+                print(f"PeerAllReduce unavailable: {e}; using NCCL", file=sys.stderr)
+            ok = torch.tensor([1 if self.peer_ar is not None else 0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:                          # all ranks must agree; close() ends with a barrier
+                if self.peer_ar is not None:
+                    self.peer_ar.close()
+                    self.peer_ar = None
+                else:
+                    dist.barrier()
         if mode in ("push", "p2p", "allgather"):
             try:
                 self.exchange = ShGradExchange(self.cfg.n_gaussians, self.C, self.device, mode=mode,
@@ -296,15 +314,29 @@ class Workload:
         import torch.distributed as dist
         ex = getattr(self, "exchange", None)
         small = [v.grad.reshape(-1) for k, v in self.params.items() if k != "sh_coeffs"]
-        flat = torch.cat(small)
-        work = dist.all_reduce(flat, async_op=True)          # NCCL stream: overlaps the gather kernel below
+        work = None
+        if self.peer_ar is not None:
+            # pack straight into the peer-visible buffer, reduce on a side stream so that it overlaps the gather kernel
+            n = sum(t.numel() for t in small)
+            flat = self.peer_ar.flat[:n]
+            torch.cat(small, out=flat)
+            main = torch.cuda.current_stream(self.device)
+            self.ar_stream.wait_stream(main)
+            with torch.cuda.stream(self.ar_stream):
+                self.peer_ar.all_reduce()
+        else:
+            flat = torch.cat(small)
+            work = dist.all_reduce(flat, async_op=True)      # NCCL stream: overlaps the gather kernel below
         if ex is not None:
             self.params["sh_coeffs"].grad = ex.finish()
         else:
             for w in self.pending:
                 w.wait()
             self.pending.clear()
-        work.wait()
+        if work is not None:
+            work.wait()
+        else:
+            torch.cuda.current_stream(self.device).wait_stream(self.ar_stream)
         return flat
 
 
@@ -589,7 +621,8 @@ def multi_gpu_diagnostics(wl, world, device, lib, backend, resident, push_engine
     torch.cuda.synchronize(device)
     spans = backend.timing_collect()
     lib.rs_timing_enable(0)
-    keys = ("rs_sh_colors_bwd_local", "rs_peer_signal", "rs_peer_wait", "rs_sh_coeffs_gather", "rs_sh_colors_bwd")
+    keys = ("rs_sh_colors_bwd_local", "rs_peer_signal", "rs_peer_wait", "rs_sh_coeffs_gather", "rs_sh_colors_bwd",
+            "rs_peer_allreduce")
     return {"compute_only_ms_per_rank": [round(float(v[0]), 4) for v in everyone],
             "n_isects_per_rank": [int(v[1]) for v in everyone],
             "exchange_spans_ms_rank0": {k: round(spans[k][0] / 5, 4) for k in keys if k in spans},
@@ -607,7 +640,7 @@ def run_config4(args, device, rank, world, lib, backend):
     total = 8
     wl = Workload(4, device, rank, world, total_views=total)
     if world > 1:
-        wl.push_engine, wl.push_ctas = args.push_engine, args.push_ctas
+        wl.push_engine, wl.push_ctas, wl.small_allreduce = args.push_engine, args.push_ctas, args.small_allreduce
         wl.enable_grad_exchange(args.grad_exchange)
 
     def resident():
@@ -638,6 +671,10 @@ def run_config4(args, device, rank, world, lib, backend):
         if getattr(wl, "exchange", None) is not None:
             wl.exchange.check()
             wl.exchange.close()
+        if getattr(wl, "peer_ar", None) is not None:
+            wl.peer_ar.check()
+            wl.peer_ar.close()
+        out["small_grad_allreduce"] = "peer kernel (rs_peer_allreduce)" if getattr(wl, "peer_ar", None) is not None else "nccl"
         dist.barrier()
     if rank == 0:
         lib.rs_timing_enable(1)
@@ -752,6 +789,9 @@ def main():
     ap.add_argument("--grad-exchange", default="push", choices=["push", "p2p", "allgather", "allreduce"],
                     help="N > 1: how the SH-coefficient gradients are combined (default: copy-engine push into peer "
                          "inboxes + local gather kernel; p2p = gather kernel pulls over NVLink)")
+    ap.add_argument("--small-allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the non-SH parameter gradients (44 B per Gaussian) are summed: the two-shot peer-memory "
+                         "kernel (rs_peer_allreduce) or NCCL")
     ap.add_argument("--push-engine", default="dma", choices=["dma", "sm"],
                     help="push exchange: copy engines (cudaMemcpyAsync per peer) or one SM store kernel (rs_peer_push)")
     ap.add_argument("--push-ctas", type=int, default=4, help="CTAs per peer of the SM store kernel")
@@ -794,7 +834,7 @@ def main():
     wl = Workload(args.config, device, rank, world)
     wl.fused_loss = not args.torch_loss
     if world > 1:
-        wl.push_engine, wl.push_ctas = args.push_engine, args.push_ctas
+        wl.push_engine, wl.push_ctas, wl.small_allreduce = args.push_engine, args.push_ctas, args.small_allreduce
         wl.enable_grad_exchange(args.grad_exchange)
 
     def resident_flat():
@@ -863,6 +903,11 @@ def main():
         wl.exchange.check()
         wl.exchange.close()
         wl.exchange = None
+    if world > 1 and getattr(wl, "peer_ar", None) is not None:
+        multi["small_grad_allreduce"] = "peer kernel (rs_peer_allreduce)"
+        wl.peer_ar.check()
+        wl.peer_ar.close()
+        wl.peer_ar = None
     if rank == 0:
         # per-kernel device time measured INSIDE real steps (same inputs, same cache state): the library
         # brackets every entry point with CUDA events on the launching stream

@@ -50,7 +50,57 @@ __global__ void __launch_bounds__(256) peer_push_kernel(PushDsts d, const uint4*
   for (; i < n16; i += stride) dst[i] = __ldg(src + i);
 }
 
+struct ArBufs {
+  float4* buf[16];
+};
+
+// Two-shot all-reduce (sum) over peer-mapped buffers, in place, in ONE kernel: rank r owns slice r of the vector.
+// Shot 1 (reduce-scatter by pull): it reads slice r of every rank's buffer over NVLink and adds them in rank order
+// 0..G-1 -- one fixed order, computed once, so every replica ends up with bit-identical sums.  Shot 2 (all-gather by
+// push): it stores the sum into slice r of every rank's buffer.  Slice g of any buffer is read and written by rank g
+// only, so no buffer is touched by two ranks at once; the caller brackets the kernel with the flag handshake
+// (rs_peer_signal / rs_peer_wait): "all inputs are in place" before, "all sums have landed" after.
+template <int G>
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(ArBufs b, int rank, long long slice4) {
+  const long long lo = (long long)rank * slice4;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < slice4; i += stride) {
+    float4 v[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[g] = b.buf[g][lo + i];   // G independent loads in flight (G - 1 of them over NVLink)
+    float4 acc = v[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) { acc.x += v[g].x; acc.y += v[g].y; acc.z += v[g].z; acc.w += v[g].w; }
+#pragma unroll
+    for (int g = 0; g < G; ++g) b.buf[g][lo + i] = acc;     // posted stores
+  }
+}
+
 }  // namespace
+
+// In-place sum of `n_floats` fp32 values over n_ranks peer-mapped buffers (bufs: HOST array, bufs[g] = rank g's buffer
+// as mapped in this process, bufs[my_rank] = the local one).  n_floats must be a multiple of 4 * n_ranks (pad with
+// zeros); n_ranks in {2, 4, 8}.  The caller orders it with the flag handshake: every rank has finished writing its
+// buffer before any rank launches this, and nobody reads a buffer before every rank's launch has completed.
+extern "C" int rs_peer_allreduce(void* const* bufs, int n_ranks, int my_rank, long long n_floats, int ctas,
+                                 void* stream) {
+  RsSpan span__("rs_peer_allreduce", stream);
+  if (!bufs || my_rank < 0 || my_rank >= n_ranks || n_floats < 0 || ctas <= 0) return RS_ERR_BAD_ARG;
+  if (n_ranks != 2 && n_ranks != 4 && n_ranks != 8) return RS_ERR_UNSUPPORTED;
+  if (n_floats % (4ll * n_ranks)) return RS_ERR_BAD_ARG;
+  if (n_floats == 0) return RS_OK;
+  ArBufs b;
+  for (int g = 0; g < n_ranks; ++g) {
+    if (!bufs[g]) return RS_ERR_BAD_ARG;
+    b.buf[g] = (float4*)bufs[g];
+  }
+  const long long slice4 = n_floats / 4 / n_ranks;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_ranks == 2) peer_allreduce_kernel<2><<<ctas, 256, 0, st>>>(b, my_rank, slice4);
+  else if (n_ranks == 4) peer_allreduce_kernel<4><<<ctas, 256, 0, st>>>(b, my_rank, slice4);
+  else peer_allreduce_kernel<8><<<ctas, 256, 0, st>>>(b, my_rank, slice4);
+  RS_RETURN_LAST_ERROR();
+}
 
 extern "C" int rs_peer_alloc(long long bytes, void** ptr) {
   if (bytes <= 0 || !ptr) return RS_ERR_BAD_ARG;

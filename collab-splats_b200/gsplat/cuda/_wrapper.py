@@ -240,7 +240,9 @@ def isect_tiles(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, 
     tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
     cum = torch.empty(max(n_elems, 1), device=dev, dtype=torch.int64)
     tile_bits = lib.rs_tile_bits(tile_width, tile_height)
-    cam_bits = int(math.floor(math.log2(C))) + 1
+    # the key layout reserves floor(log2 C) + 1 camera bits (gsplat), but camera ids only reach C - 1: the sort stops at
+    # the highest bit that can be set (C = 8: 16 instead of 17 key bits above the depth -> two 8-bit passes, not three)
+    cam_bits = max(int(C - 1).bit_length(), 0)
     end_bit = 32 + tile_bits + cam_bits
     presort = sort and ISECT_SORT_METHOD == "presort" and n_elems > 0
     with torch.cuda.device(dev):
@@ -641,7 +643,10 @@ class _RasterizeToPixels(torch.autograd.Function):
                     _be.check(lib.rs_unpack_colors_grad(_be.ptr(color_grad), rows, D, DP, _be.ptr(v_col), st),
                               "rs_unpack_colors_grad")
         if absgrad and ctx.means2d_ref is not None:
-            ctx.means2d_ref.absgrad = v_abs
+            # a render with more than 72 channels runs one compositing pass per channel chunk over the SAME means2d:
+            # the chunks' |gradient| sums add up (rasterization() clears the attribute before the passes)
+            prev = getattr(ctx.means2d_ref, "absgrad", None)
+            ctx.means2d_ref.absgrad = v_abs if prev is None else prev + v_abs
         v_bg = None
         if backgrounds is not None and ctx.needs_input_grad[8]:
             v_bg = (v_colors * out_T[..., None]).sum(dim=(1, 2))

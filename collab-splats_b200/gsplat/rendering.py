@@ -135,7 +135,9 @@ def rasterization(
             backgrounds=backgrounds, absgrad=absgrad, ray_ts=ray_ts, ray_planes=ray_planes, normals=normals, Ks=Ks,
             compensations=compensations, ed_channel=(D - 1) if ed else -1)
     else:
-        chunk = 64
+        chunk = min(max(int(channel_chunk), 1), 64) if channel_chunk > 32 else 64   # (upstream's default 32 -> one 64-wide pass)
+        if absgrad and hasattr(means2d, "absgrad"):
+            del means2d.absgrad        # the chunks' backward passes accumulate into it
         parts = []
         render_alphas = exp_d = med_d = nrm = None
         for k0 in range(0, D, chunk):

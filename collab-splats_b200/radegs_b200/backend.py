@@ -81,6 +81,7 @@ _SIGNATURES = {
     "rs_peer_unimport": (_i, [_p]),
     "rs_peer_copy": (_i, [_p, _p, _ll, _p]),
     "rs_peer_push": (_i, [_p, _i, _p, _ll, _i, _p]),
+    "rs_peer_allreduce": (_i, [_p, _i, _i, _ll, _i, _p]),
     "rs_peer_signal": (_i, [_p, _i, _i, C.c_ulonglong, _p]),
     "rs_peer_wait": (_i, [_p, _i, C.c_ulonglong, _i, _p, _p]),
     "rs_densify_stats": (_i, [_p, _p, _i, _i, _f, _f, _f, _p, _p, _p, _p]),

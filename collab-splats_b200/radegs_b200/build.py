@@ -67,7 +67,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+    # --cudart shared: the library resolves the CUDA runtime torch has already loaded (libcudart.so.12) instead of
+    # embedding a static copy of every runtime entry point
+    cmd = [nvcc, "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
            *[str(o) for o in objs], "-o", str(LIB_PATH)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -49,7 +49,7 @@ class _FusedRadeLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, render, alphas, exp_depth, med_depth, normals, gt_u8, K, background, lam, depth_ratio,
-                use_depth_normal):
+                use_depth_normal, l1_weight):
         from . import backend as _be
         lib = _be.load()
         H, W, D = render.shape
@@ -61,7 +61,7 @@ class _FusedRadeLoss(torch.autograd.Function):
         v_exp = torch.zeros_like(exp_depth)
         v_med = torch.zeros_like(med_depth)
         v_nrm = torch.empty_like(normals)
-        w_l1 = 1.0 / (3.0 * P)
+        w_l1 = l1_weight / (3.0 * P)
         w_exp = lam * (1.0 - depth_ratio) / P if use_depth_normal else 0.0
         w_med = lam * depth_ratio / P if use_depth_normal else 0.0
         fx, fy = K
@@ -72,6 +72,7 @@ class _FusedRadeLoss(torch.autograd.Function):
                 _be.ptr(sums), _be.ptr(v_render), _be.ptr(v_alphas), _be.ptr(v_exp), _be.ptr(v_med), _be.ptr(v_nrm),
                 _be.stream_ptr(dev)), "rs_rade_loss_fwd_bwd")
         ctx.save_for_backward(v_render, v_alphas, v_exp, v_med, v_nrm)
+        ctx.set_materialize_grads(False)             # an unused output's gradient arrives as None (see backward)
         return sums[3], sums                         # loss, (l1, dn_expected, dn_median, loss)
 
     @staticmethod
@@ -82,25 +83,34 @@ class _FusedRadeLoss(torch.autograd.Function):
         # would need retain_graph and is not supported).  Gradients w.r.t. the individual terms are not supported:
         # differentiate the total.
         from . import backend as _be
+        if g_terms is not None:
+            raise NotImplementedError("fused_rade_loss: the individual terms are reported, not differentiable -- "
+                                      "differentiate the total loss")
+        if g_loss is None:
+            return (None,) * 12
         if getattr(ctx, "_consumed", False):
             raise RuntimeError("fused_rade_loss: a second backward through the same graph is not supported "
                                "(the gradient buffers are scaled in place)")
         ctx._consumed = True
         out = list(ctx.saved_tensors)
         _be.scale_unless_one(out, g_loss)
-        return (*out, None, None, None, None, None, None)
+        return (*out, None, None, None, None, None, None, None)
 
 
 def fused_rade_loss(render: Tensor, alphas: Tensor, expected_depth: Tensor, median_depth: Tensor,
                     rendered_normals: Tensor, gt_rgb_u8: Tensor, fx: float, fy: float,
                     background: Tensor = None, lam: float = 0.05, depth_ratio: float = 0.6,
-                    use_depth_normal: bool = True):
+                    use_depth_normal: bool = True, l1_weight: float = 1.0):
     """One camera: render [H,W,D>=3], alphas / depths [H,W], normals [H,W,3], gt uint8 [H,W,3] ->
     (loss, terms[4] = (L1, dn_expected, dn_median, loss)).  Same arithmetic as ``(clamp(rgb)-gt).abs().mean() +
     depth_normal_loss(...)`` above, fused with its own backward.  `fx, fy` are host floats (the principal point
-    is the image centre, rade_gs_model.py:327-334) so no device->host read is needed."""
+    is the image centre, rade_gs_model.py:327-334) so no device->host read is needed.
+
+    ``l1_weight`` scales the L1 term: the reference's rgb loss is ``(1 - ssim_lambda) * L1 + ssim_lambda * (1 - SSIM)``
+    with ssim_lambda = 0.2 (nerfstudio's SplatfactoModel.get_loss_dict, reached through rade_gs_model.py:289); pass
+    0.8 and add the SSIM term (host-framework code, not part of this path) to reproduce that objective."""
     assert render.dim() == 3 and render.shape[-1] >= 3 and gt_rgb_u8.dtype == torch.uint8
     c = lambda t: t.contiguous()
     return _FusedRadeLoss.apply(c(render), c(alphas), c(expected_depth), c(median_depth), c(rendered_normals),
                                 c(gt_rgb_u8), (float(fx), float(fy)), None if background is None else c(background),
-                                float(lam), float(depth_ratio), bool(use_depth_normal))
+                                float(lam), float(depth_ratio), bool(use_depth_normal), float(l1_weight))

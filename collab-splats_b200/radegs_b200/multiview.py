@@ -325,3 +325,107 @@ class ShGradExchange:
         """Raises if a peer failed to publish within the timeout (one device->host read: call it off the hot path)."""
         if int(self.timed_out.item()) != 0:
             raise RuntimeError("ShGradExchange: a peer rank did not publish its colour gradients in time")
+
+
+class _RawCudaBuffer:
+    """Lets torch view a raw device pointer (peer-visible memory from rs_peer_alloc) as a tensor."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (int(n_floats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerAllReduce:
+    """Sum of one flat fp32 vector over the ranks WITHOUT NCCL: the two-shot all-reduce kernel of csrc/peer.cu
+    (``rs_peer_allreduce``) over CUDA-IPC-mapped buffers, bracketed by the flag handshake.
+
+    ``self.flat`` is a torch view of this rank's peer-visible buffer: write the local values into it (e.g.
+    ``torch.cat(grads, out=ar.flat[:n])``), call ``all_reduce()``, read the sums from the same tensor.  Every rank adds
+    the contributions in rank order, once per slice, so all replicas hold bit-identical results.  Per step each rank
+    moves (G-1)/G of the vector in over NVLink and the same amount out (the ring all-reduce's volume) in one kernel.
+    """
+
+    def __init__(self, n_floats: int, device, group=None, ctas: int = 296, timeout_ms: int = 5000):
+        from radegs_b200 import backend as be
+        import ctypes
+        self.be, self.ct, self.lib = be, ctypes, be.load()
+        self.device = torch.device(device)
+        self.group = group
+        ready = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if ready else 1
+        self.rank = dist.get_rank(group) if ready else 0
+        if self.world not in (1, 2, 4, 8):
+            raise NotImplementedError("PeerAllReduce supports 1, 2, 4 or 8 ranks")
+        quantum = 4 * self.world
+        self.n = (int(n_floats) + quantum - 1) // quantum * quantum
+        self.ctas, self.timeout_ms = int(ctas), int(timeout_ms)
+        self.step = 0
+        self._peer_ptrs, self._own = [], []
+        ct, lib = ctypes, self.lib
+        with torch.cuda.device(self.device):
+            ptrs = []
+            for nbytes in (4 * self.n, 256, 256):            # data, "inputs ready" flags, "sums landed" flags
+                p = ct.c_void_p()
+                be.check(lib.rs_peer_alloc(nbytes, ct.byref(p)), "rs_peer_alloc")
+                self._own.append(p.value)
+                ptrs.append(p.value)
+            hb = lib.rs_peer_handle_bytes()
+            handles = []
+            for ptr in ptrs:
+                buf = ct.create_string_buffer(hb)
+                be.check(lib.rs_peer_export(ct.c_void_p(ptr), buf), "rs_peer_export")
+                handles.append(bytes(buf.raw))
+            everyone = [handles]
+            if self.world > 1:
+                everyone = [None] * self.world
+                dist.all_gather_object(everyone, handles, group=group)
+            self.bases = [[], [], []]
+            for g, hs in enumerate(everyone):
+                for k, h in enumerate(hs):
+                    if g == self.rank:
+                        self.bases[k].append(ptrs[k])
+                        continue
+                    p = ct.c_void_p()
+                    be.check(lib.rs_peer_import(ct.create_string_buffer(h, hb), ct.byref(p)), "rs_peer_import")
+                    self._peer_ptrs.append(p.value)
+                    self.bases[k].append(p.value)
+            self.flat = torch.as_tensor(_RawCudaBuffer(ptrs[0], self.n), device=self.device)
+            self.ready_dev = torch.tensor(self.bases[1], dtype=torch.int64, device=self.device)
+            self.done_dev = torch.tensor(self.bases[2], dtype=torch.int64, device=self.device)
+            self.timed_out = torch.zeros(1, device=self.device, dtype=torch.int32)
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    @torch.no_grad()
+    def all_reduce(self) -> Tensor:
+        """Sums ``self.flat`` over the ranks in place, on the current stream; returns ``self.flat``."""
+        if self.world == 1:
+            return self.flat
+        be, lib, ct = self.be, self.lib, self.ct
+        self.step += 1
+        with torch.cuda.device(self.device):
+            st = be.stream_ptr(self.device)
+            be.check(lib.rs_peer_signal(be.ptr(self.ready_dev), self.world, self.rank, self.step, st), "rs_peer_signal")
+            be.check(lib.rs_peer_wait(ct.c_void_p(self.bases[1][self.rank]), self.world, self.step, self.timeout_ms,
+                                      be.ptr(self.timed_out), st), "rs_peer_wait")
+            bufs = (ct.c_void_p * self.world)(*self.bases[0])
+            be.check(lib.rs_peer_allreduce(bufs, self.world, self.rank, self.n, self.ctas, st), "rs_peer_allreduce")
+            be.check(lib.rs_peer_signal(be.ptr(self.done_dev), self.world, self.rank, self.step, st), "rs_peer_signal")
+            be.check(lib.rs_peer_wait(ct.c_void_p(self.bases[2][self.rank]), self.world, self.step, self.timeout_ms,
+                                      be.ptr(self.timed_out), st), "rs_peer_wait")
+        return self.flat
+
+    def check(self):
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError("PeerAllReduce: a peer rank did not arrive in time")
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_available() and dist.is_initialized() and self.world > 1:
+            dist.barrier(group=self.group)
+        self.flat = None
+        for p in self._peer_ptrs:
+            self.lib.rs_peer_unimport(self.ct.c_void_p(p))
+        for p in self._own:
+            self.lib.rs_peer_free(self.ct.c_void_p(p))
+        self._peer_ptrs, self._own = [], []

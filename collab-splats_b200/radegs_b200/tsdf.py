@@ -170,7 +170,11 @@ def fuse_render_sweep(volume: ScalableTSDFVolume, gaussians, viewmats: Tensor, K
     ``views_per_launch`` > 1 renders that many cameras per ``rasterization`` call (the camera axis of the
     rasterizer; identical frames, fewer launches); frames are integrated in camera order either way.
     Returns the number of frames integrated.  No per-frame host synchronisation besides the rasterizer's own
-    intersection-count read."""
+    intersection-count read; the volume's overflow counter is checked once after the last frame (a full unit pool
+    would otherwise drop units silently for the whole sweep).  Triangle extraction (the reference's next call,
+    ``volume.extract_triangle_mesh()``, mesh.py:1632) is NOT provided: the marching-cubes tables are not available
+    offline; ``ScalableTSDFVolume.units()`` / ``extract_voxel_point_cloud()`` export (xyz, tsdf, weight, rgb) for an
+    Open3D or skimage marching-cubes pass on the host."""
     from gsplat.rendering import rasterization
     if depth_name not in ("depth", "median_depth"):
         raise ValueError("depth_name must be 'depth' or 'median_depth'")
@@ -193,4 +197,5 @@ def fuse_render_sweep(volume: ScalableTSDFVolume, gaussians, viewmats: Tensor, K
             for v in range(v0, v1):
                 intr = PinholeCameraIntrinsic(width, height, Kh[v, 0, 0], Kh[v, 1, 1], Kh[v, 0, 2], Kh[v, 1, 2])
                 volume.integrate(d[v - v0], rgb8[v - v0], intr, ext[v], depth_trunc=depth_trunc)
+    volume.n_units()          # one read-back at the END of the sweep: raises if the unit pool overflowed on any frame
     return V

@@ -220,6 +220,12 @@ int rs_peer_copy(void* dst, const void* src, long long bytes, void* stream);
 /* the same transfer to n_dst <= 16 peers (dsts: HOST array of peer-mapped device pointers; bytes % 16 == 0) driven by
  * the SMs: one kernel, ctas_per_dst CTAs per destination, 16-byte posted stores over NVLink */
 int rs_peer_push(void* const* dsts, int n_dst, const void* src, long long bytes, int ctas_per_dst, void* stream); /* copy engines, peer pointers ok */
+/* Two-shot all-reduce (sum, in place) of n_floats fp32 values over the ranks' peer-mapped buffers in one kernel: rank r
+ * pulls slice r of every buffer over NVLink, adds them in rank order (bit-identical results on every rank) and pushes
+ * the sum into slice r of every buffer.  Replaces the NCCL all-reduce of the small Gaussian-parameter gradients
+ * (SURVEY.md 8e).  bufs: HOST array of n_ranks (2, 4 or 8) pointers; n_floats % (4 * n_ranks) == 0.  The caller brackets
+ * it with rs_peer_signal / rs_peer_wait on both sides. */
+int rs_peer_allreduce(void* const* bufs, int n_ranks, int my_rank, long long n_floats, int ctas, void* stream);
 int rs_peer_signal(void* const* flag_arrays_dev, int n_ranks, int my_rank, unsigned long long value, void* stream);
 int rs_peer_wait(const void* local_flags, int n_ranks, unsigned long long value, int timeout_ms, int* timed_out_dev,
                  void* stream);
