@@ -261,7 +261,7 @@ class Workload:
         self.exchange, self.exchange_mode = None, mode
         self.collectives_on = True
         self.peer_ar = None
-        if getattr(self, "small_allreduce", "peer") == "peer" and dist.get_world_size() in (2, 4, 8):
+        if getattr(self, "small_allreduce", "nccl") == "peer" and dist.get_world_size() in (2, 4, 8):
             # the 11 floats per Gaussian that are not SH coefficients: two-shot all-reduce kernel over peer memory
             from radegs_b200.multiview import PeerAllReduce
             n_small = sum(v.numel() for k, v in self.params.items() if k != "sh_coeffs")
@@ -281,8 +281,8 @@ class Workload:
         if mode in ("push", "p2p", "allgather"):
             try:
                 self.exchange = ShGradExchange(self.cfg.n_gaussians, self.C, self.device, mode=mode,
-                                               push_engine=getattr(self, "push_engine", "dma"),
-                                               push_ctas=getattr(self, "push_ctas", 4))
+                                               push_engine=getattr(self, "push_engine", "sm"),
+                                               push_ctas=getattr(self, "push_ctas", 0))
             except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC unavailable in this container)
                 print(f"ShGradExchange({mode}) unavailable: {e}; falling back to all-reduce", file=sys.stderr)
                 self.exchange_mode = "allreduce"
@@ -789,12 +789,14 @@ def main():
     ap.add_argument("--grad-exchange", default="push", choices=["push", "p2p", "allgather", "allreduce"],
                     help="N > 1: how the SH-coefficient gradients are combined (default: copy-engine push into peer "
                          "inboxes + local gather kernel; p2p = gather kernel pulls over NVLink)")
-    ap.add_argument("--small-allreduce", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: how the non-SH parameter gradients (44 B per Gaussian) are summed: the two-shot peer-memory "
-                         "kernel (rs_peer_allreduce) or NCCL")
-    ap.add_argument("--push-engine", default="dma", choices=["dma", "sm"],
-                    help="push exchange: copy engines (cudaMemcpyAsync per peer) or one SM store kernel (rs_peer_push)")
-    ap.add_argument("--push-ctas", type=int, default=4, help="CTAs per peer of the SM store kernel")
+    ap.add_argument("--small-allreduce", default="nccl", choices=["peer", "nccl"],
+                    help="N > 1: how the non-SH parameter gradients (44 B per Gaussian) are summed: NCCL (default) or the "
+                         "two-shot peer-memory kernel (rs_peer_allreduce; exact and replica-identical, but measured slower "
+                         "inside the step at N = 2 and N = 8, profiles/r02_exchange_ab_n8.txt)")
+    ap.add_argument("--push-engine", default="sm", choices=["dma", "sm"],
+                    help="push exchange: one SM store kernel (rs_peer_push, default) or the copy engines "
+                         "(cudaMemcpyAsync per peer)")
+    ap.add_argument("--push-ctas", type=int, default=0, help="CTAs per peer of the SM store kernel (0 = by payload)")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline config only: skip the config-4 / config-5 / config-1 blocks (quick A/B runs)")
     ap.add_argument("--profile-step", action="store_true",

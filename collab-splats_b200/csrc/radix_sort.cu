@@ -226,12 +226,17 @@ static int sort_pairs_impl(K* ka, u32* va, K* kb, u32* vb, bool iota_vals, long 
   cudaStream_t st = (cudaStream_t)stream;
   PassInfo pi;
   pi.n = npass;
-  for (int p = 0; p < MAX_PASSES; ++p) {
-    int sh = begin_bit + p * RADIX_BITS;
-    int nb = end_bit - sh;
-    if (nb > RADIX_BITS) nb = RADIX_BITS;
-    pi.shift[p] = p < npass ? sh : 0;
-    pi.mask[p] = p < npass ? ((1u << nb) - 1u) : 0u;
+  // the key bits are split EVENLY over the passes (13 tile bits: 7 + 6, not 8 + 5): fewer bins in the wide pass mean
+  // longer runs per bin in every block's output, i.e. fuller sectors on the scattered writes
+  {
+    int sh = begin_bit;
+    for (int p = 0; p < MAX_PASSES; ++p) {
+      int nb = 0;
+      if (p < npass) nb = (end_bit - sh + (npass - p) - 1) / (npass - p);
+      pi.shift[p] = p < npass ? sh : 0;
+      pi.mask[p] = p < npass ? ((1u << nb) - 1u) : 0u;
+      sh += nb;
+    }
   }
   const int items = g_sort_items;
   const long long nblocks = sort_blocks(M, items);

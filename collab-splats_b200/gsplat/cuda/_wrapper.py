@@ -32,8 +32,7 @@ ISECT_SORT_METHOD = "presort"
 #   "compact": depth argsort, (camera|tile u32, flatten id) pairs through two radix passes, 64-bit keys and offsets
 #            rebuilt together after the sort (8-byte instead of 12-byte pairs): the radix passes gain 7 % (they are
 #            latency-bound), the rebuild costs more than offset_encode alone -> 0.389 vs 0.378 ms, not the default
-#   "chunk": per-camera depth argsort + chunked counting sort (csrc/chunksort.cu), no radix passes over the pairs
-#            (measured slower: scattered 12-byte stores, profiles/r01_chunk_ab.txt);  "tile": csrc/tilesort.cu
+#   (a chunked counting sort and a tile-partitioned bitonic sort were measured slower: experiments/)
 ISECT_PIPELINE = "radix"
 # Compositing options (backend.RS_RASTER_* bits, 0 = defaults) and optional work counters (a 4 x int64 device tensor,
 # <= 4 channels) that rasterize_to_pixels passes with every call.  They are read when the forward runs and travel
@@ -347,71 +346,16 @@ def _isect_compact(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: i
     return tiles, ids, flat, offsets
 
 
-def _isect_chunked(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int):
-    """csrc/chunksort.cu: tiles_per_gauss, sorted isect_ids / flatten_ids and isect_offsets without sorting the pairs."""
-    lib = _be.load()
-    C, N = depths.shape
-    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
-    _need_cuda(means2d, radii, depths)
-    dev = means2d.device
-    means2d, depths = _c(means2d), _c(depths)
-    radii = _c(radii, torch.int32)
-    T = tile_width * tile_height
-    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
-    G = lib.rs_isect_chunk_size(C, N)
-    cpc = (N + G - 1) // G
-    Tpad = (T + 1) // 2 * 2
-    order = torch.empty(C, N, device=dev, dtype=torch.int32)
-    with torch.cuda.device(dev):
-        st = _be.stream_ptr(dev)
-        _be.check(lib.rs_isect_count(_be.ptr(means2d), _be.ptr(radii), C * N, tile_width, tile_height,
-                                     _be.ptr(tiles), st), "rs_isect_count")
-        dkeys = depths.clone().view(torch.int32)              # the sort clobbers its key buffers
-        dkeys_b = torch.empty(N, device=dev, dtype=torch.int32)
-        ord_b = torch.empty(N, device=dev, dtype=torch.int32)
-        sb = lib.rs_sort_pairs_temp_bytes(N, 0, 32)
-        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
-        for c in range(C):                                    # one stable argsort per camera (ties keep index order)
-            where = _be.check(lib.rs_argsort_u32(_be.ptr(dkeys[c]), _be.ptr(order[c]), _be.ptr(dkeys_b), _be.ptr(ord_b),
-                                                 N, 0, 32, _be.ptr(stemp), sb, st), "rs_argsort_u32")
-            if where == 0:
-                order[c].copy_(ord_b)
-        H = torch.empty(C * cpc, Tpad, device=dev, dtype=torch.int16)
-        tot = torch.empty(C * T, device=dev, dtype=torch.int32)
-        _be.check(lib.rs_isect_chunk_count(_be.ptr(means2d), _be.ptr(radii), _be.ptr(order), C, N, tile_width,
-                                           tile_height, G, _be.ptr(H), _be.ptr(tot), st), "rs_isect_chunk_count")
-        incl = torch.empty(C * T, device=dev, dtype=torch.int64)
-        tb = lib.rs_cumsum_temp_bytes(C * T)
-        temp = torch.empty(tb, device=dev, dtype=torch.uint8)
-        _be.check(lib.rs_cumsum_i32_i64(_be.ptr(tot), _be.ptr(incl), C * T, _be.ptr(temp), tb, st), "rs_cumsum_i32_i64")
-        base = torch.empty(C * cpc, Tpad, device=dev, dtype=torch.int32)
-        offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
-        _be.check(lib.rs_isect_chunk_base(_be.ptr(H), _be.ptr(tot), _be.ptr(incl), C, N, tile_width, tile_height, G,
-                                          _be.ptr(base), _be.ptr(offsets), st), "rs_isect_chunk_base")
-        M = int(incl[C * T - 1].item())
-        ids = torch.empty(M, device=dev, dtype=torch.int64)
-        flat = torch.empty(M, device=dev, dtype=torch.int32)
-        if M > 0:
-            _be.check(lib.rs_isect_chunk_emit(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), _be.ptr(order), C, N,
-                                              tile_width, tile_height, G, _be.ptr(base), _be.ptr(ids), _be.ptr(flat),
-                                              st), "rs_isect_chunk_emit")
-    return tiles, ids, flat, offsets
-
-
 @torch.no_grad()
 def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile_size: int, tile_width: int,
                             tile_height: int, method: Optional[str] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """``isect_tiles(sort=True)`` + ``isect_offset_encode`` in one go.
     -> tiles_per_gauss [C,N] i32, isect_ids [M] i64, flatten_ids [M] i32, isect_offsets [C,TH,TW] i32.
 
-    ``method=None``: the module default ``ISECT_PIPELINE`` ("radix").  ``method="compact"``: the presorted path with
-    32-bit camera|tile keys through the radix passes (falls back to "radix" when camera|tile needs more than 32 bits).  ``method="radix"``: emit + onesweep radix
-    sort + offset encode.  ``method="chunk"``: per-camera depth argsort + chunked counting sort (csrc/chunksort.cu).  ``method="tile"``: the
-    tile-partitioned path of csrc/tilesort.cu (per-tile histogram -> offsets, atomic-slot emission into tile
-    segments, per-tile shared-memory bitonic sort; falls back to radix when a tile holds more than
-    ``rs_tile_sort_max_segment()`` intersections).  Both are bit-identical (tests check it); on B200 at BASELINE
-    config 2 the tile path moves 5x fewer bytes but measured SLOWER (0.79 ms vs 0.61 ms: 6.9 M atomics in count
-    and emit cost 0.35 ms, the bitonic network 0.43 ms), so it is not the default -- see DESIGN.md."""
+    ``method=None``: the module default ``ISECT_PIPELINE`` ("radix": emit + onesweep radix sort + offset encode).
+    ``method="compact"``: the presorted path with 32-bit camera|tile keys through the radix passes (falls back to "radix"
+    when camera|tile needs more than 32 bits).  Both are bit-identical (tests check it).  Two further pipelines (a
+    tile-partitioned bitonic sort and a chunked counting sort) were measured slower and live under ``experiments/``."""
     if tile_size != TILE_SIZE:
         raise NotImplementedError("tile_size must be 16")
     if method is None:
@@ -423,49 +367,11 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
             method = "radix"
         else:
             return _isect_compact(means2d, radii, depths, tile_width, tile_height, bits)
-    if method == "chunk":
-        if tile_width * tile_height > _be.load().rs_isect_chunk_max_tiles() or depths.numel() == 0:
-            method = "radix"
-        else:
-            return _isect_chunked(means2d, radii, depths, tile_width, tile_height)
-    if method == "radix":
-        C = depths.shape[0]
-        tiles, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)
-        return tiles, ids, flat, isect_offset_encode(ids, C, tile_width, tile_height)
-    assert method == "tile", method
-    lib = _be.load()
-    C, N = depths.shape
-    assert means2d.shape == (C, N, 2) and radii.shape == (C, N, 2), (means2d.shape, radii.shape)
-    _need_cuda(means2d, radii, depths)
-    dev = means2d.device
-    means2d, depths = _c(means2d), _c(depths)
-    radii = _c(radii, torch.int32)
-    T = C * tile_width * tile_height
-    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
-    counts = torch.zeros(T, device=dev, dtype=torch.int32)
-    offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
-    cursors = torch.empty(T, device=dev, dtype=torch.int32)
-    totals = torch.empty(2, device=dev, dtype=torch.int64)
-    with torch.cuda.device(dev):
-        st = _be.stream_ptr(dev)
-        _be.check(lib.rs_isect_tile_count(_be.ptr(means2d), _be.ptr(radii), C, N, tile_width, tile_height,
-                                          _be.ptr(tiles), _be.ptr(counts), st), "rs_isect_tile_count")
-        _be.check(lib.rs_isect_tile_scan(_be.ptr(counts), T, _be.ptr(offsets), _be.ptr(cursors), _be.ptr(totals), st),
-                  "rs_isect_tile_scan")
-        M, longest = (int(v) for v in totals.tolist())
-        if longest > lib.rs_tile_sort_max_segment():
-            _, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)
-            return tiles, ids, flat, offsets
-        ids = torch.empty(M, device=dev, dtype=torch.int64)
-        flat = torch.empty(M, device=dev, dtype=torch.int32)
-        if M == 0:
-            return tiles, ids, flat, offsets
-        pairs = torch.empty(M, device=dev, dtype=torch.int64)
-        _be.check(lib.rs_isect_tile_emit(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), C, N, tile_width,
-                                         tile_height, _be.ptr(cursors), _be.ptr(pairs), st), "rs_isect_tile_emit")
-        _be.check(lib.rs_isect_tile_sort(_be.ptr(pairs), _be.ptr(offsets), C, tile_width, tile_height, M, longest,
-                                         _be.ptr(ids), _be.ptr(flat), st), "rs_isect_tile_sort")
-    return tiles, ids, flat, offsets
+    if method != "radix":
+        raise ValueError(f"unknown intersection pipeline {method!r}")
+    C = depths.shape[0]
+    tiles, ids, flat = isect_tiles(means2d, radii, depths, tile_size, tile_width, tile_height)
+    return tiles, ids, flat, isect_offset_encode(ids, C, tile_width, tile_height)
 
 
 @torch.no_grad()

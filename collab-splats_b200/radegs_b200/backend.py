@@ -41,21 +41,11 @@ _SIGNATURES = {
     "rs_cumsum_gather_i32_i64": (_i, [_p, _p, _p, _ll, _p, _ll, _p]),
     "rs_isect_emit_ordered": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_argsort_u32": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
-    "rs_tile_sort_max_segment": (_i, []),
-    "rs_isect_tile_count": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "rs_isect_tile_scan": (_i, [_p, _i, _p, _p, _p, _p]),
-    "rs_isect_tile_emit": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "rs_isect_tile_sort": (_i, [_p, _p, _i, _i, _i, _ll, _i, _p, _p, _p]),
     "rs_scale_unless_one": (_i, [_p, _p, _i, _p, _p]),
     "rs_zero_bytes": (_i, [_p, _ll, _p]),
     "rs_isect_emit_ordered32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "rs_sort_pairs_u32": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_isect_finish32": (_i, [_p, _p, _p, _ll, _i, _i, _i, _p, _p, _p]),
-    "rs_isect_chunk_size": (_i, [_i, _i]),
-    "rs_isect_chunk_max_tiles": (_i, []),
-    "rs_isect_chunk_count": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "rs_isect_chunk_base": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
-    "rs_isect_chunk_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
     "rs_sort_set_items": (None, [_i]),
     "rs_sort_set_window": (None, [_i]),

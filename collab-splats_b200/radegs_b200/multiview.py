@@ -113,7 +113,7 @@ class ShGradExchange:
     """
 
     def __init__(self, n_gaussians: int, cams_per_rank: int, device, group=None, mode: str = "push",
-                 push_engine: str = "dma", push_ctas: int = 4,
+                 push_engine: str = "sm", push_ctas: int = 0,
                  timeout_ms: int = 5000):
         from radegs_b200 import backend as be
         import ctypes
@@ -135,7 +135,11 @@ class ShGradExchange:
         self.mode = mode
         if push_engine not in ("dma", "sm"):
             raise ValueError("push_engine must be 'dma' (copy engines) or 'sm' (store kernel)")
-        self.push_engine, self.push_ctas = push_engine, int(push_ctas)
+        # CTAs per peer of the SM store kernel; 0 = by payload: 4 up to 24 MB per peer, 8 above (8 GPUs, NVSwitch: at
+        # 16 MB per peer the copy engines deliver 384 GB/s and hold the step at 2.74 ms, 4 CTAs per peer 2.60 ms; at
+        # 48 MB per peer 8 CTAs win, profiles/r02_exchange_ab_n8.txt)
+        self.push_engine = push_engine
+        self.push_ctas = int(push_ctas) if int(push_ctas) > 0 else (4 if self.region_bytes <= 24 * 2 ** 20 else 8)
         self._peer_ptrs = []        # imported mappings, closed in close()
         self._own = []              # own cudaMalloc'ed blocks
         cams = [self.C] * self.world

@@ -98,20 +98,6 @@ int rs_isect_emit_ordered(const float* means2d, const int32_t* radii, const floa
                           const long long* cum_tiles_in_order, int C, int N, int tile_w, int tile_h,
                           long long* isect_ids, int32_t* flatten_ids, void* stream);
 
-/* ---- tile-partitioned fast path for isect_tiles(sort=True) + isect_offset_encode (same outputs, bit for bit):
- * per-tile histogram -> exclusive scan = tile offsets -> atomic-slot emission of (depth<<32 | flatten id) into the
- * tile's segment -> per-tile shared-memory sort.  tile_counts must be zero-filled; totals_dev = {M, longest
- * segment}; rs_isect_tile_sort needs longest segment <= rs_tile_sort_max_segment(), else use rs_sort_pairs. */
-int rs_tile_sort_max_segment(void);
-int rs_isect_tile_count(const float* means2d, const int32_t* radii, int C, int N, int tile_w, int tile_h,
-                        int32_t* tiles_per_gauss, int32_t* tile_counts, void* stream);
-int rs_isect_tile_scan(const int32_t* tile_counts, int n_total_tiles, int32_t* offsets, int32_t* cursors,
-                       long long* totals_dev, void* stream);
-int rs_isect_tile_emit(const float* means2d, const int32_t* radii, const float* depths, int C, int N, int tile_w,
-                       int tile_h, int32_t* cursors, unsigned long long* pairs, void* stream);
-int rs_isect_tile_sort(const unsigned long long* pairs, const int32_t* offsets, int C, int tile_w, int tile_h,
-                       long long M, int max_segment, long long* isect_ids, int32_t* flatten_ids, void* stream);
-
 /* ---- radix sort: replaces cub::DeviceRadixSort::SortPairs inside isect_tiles(sort=True).
  * Stable, ascending, on key bits [begin_bit,end_bit).  Clobbers both buffer pairs.
  * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */
@@ -259,25 +245,6 @@ int rs_sort_pairs_u32(uint32_t* keys_a, int32_t* vals_a, uint32_t* keys_b, int32
                       int end_bit, void* temp, long long temp_bytes, void* stream);
 int rs_isect_finish32(const uint32_t* keys32, const int32_t* flatten_ids, const float* depths, long long M, int C,
                       int tile_w, int tile_h, long long* isect_ids, int32_t* offsets, void* stream);
-
-/* ---- chunked counting sort of the intersections (csrc/chunksort.cu): a sort-free path to the same isect_ids /
- * flatten_ids / isect_offsets as isect_tiles(sort=True) + isect_offset_encode.  `order` [C][N] i32: for each camera
- * the Gaussian indices in depth order (stable rs_argsort_u32 of that camera's depth bits).  G = entries per chunk
- * (rs_isect_chunk_size, a multiple of 256), chunks_per_cam = ceil(N / G), Tpad = tiles rounded up to even.
- *   rs_isect_chunk_count -> H u16 [C*chunks_per_cam][Tpad], tot i32 [C*tiles]
- *   caller: incl = inclusive i64 scan of tot (rs_cumsum_i32_i64); M = incl[C*tiles - 1]
- *   rs_isect_chunk_base  -> base u32 [C*chunks_per_cam][Tpad], offsets i32 [C*tiles] (= isect_offsets)
- *   rs_isect_chunk_emit  -> isect_ids i64 [M], flatten_ids i32 [M], already sorted
- * RS_ERR_UNSUPPORTED when tiles > rs_isect_chunk_max_tiles(): use the radix path. */
-int rs_isect_chunk_size(int C, int N);
-int rs_isect_chunk_max_tiles(void);
-int rs_isect_chunk_count(const float* means2d, const int32_t* radii, const int32_t* order, int C, int N, int tile_w,
-                         int tile_h, int G, unsigned short* H, int32_t* tot, void* stream);
-int rs_isect_chunk_base(const unsigned short* H, const int32_t* tot, const long long* incl, int C, int N, int tile_w,
-                        int tile_h, int G, unsigned int* base, int32_t* offsets, void* stream);
-int rs_isect_chunk_emit(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order, int C,
-                        int N, int tile_w, int tile_h, int G, const unsigned int* base, long long* isect_ids,
-                        int32_t* flatten_ids, void* stream);
 
 /* ---- TSDF fusion of rendered frames on the device: replaces, in the meshing exporter
  * collab_splats/utils/mesh.py:1562-1632, the per-frame `.cpu().numpy()` + Open3D ScalableTSDFVolume.integrate (CPU).

@@ -7,9 +7,16 @@ run() {  # tag, extra args
       bench.py --gpus $NG --steps 20 --warmup 3 $2 > gpurun_out/r2_bench_n${NG}_$1.json 2> gpurun_out/r2_bench_n${NG}_$1.err
   echo "$1 rc $?"
 }
-run nccl_dma "--small-allreduce nccl --push-engine dma"
-run peer_dma "--small-allreduce peer --push-engine dma"
-run peer_sm "--small-allreduce peer --push-engine sm --push-ctas 8"
+for v in ${VARIANTS:-nccl_dma peer_dma peer_sm}; do
+  case $v in
+    nccl_dma) run $v "--small-allreduce nccl --push-engine dma" ;;
+    peer_dma) run $v "--small-allreduce peer --push-engine dma" ;;
+    peer_sm) run $v "--small-allreduce peer --push-engine sm --push-ctas 8" ;;
+    nccl_sm4) run $v "--small-allreduce nccl --push-engine sm --push-ctas 4" ;;
+    nccl_sm8) run $v "--small-allreduce nccl --push-engine sm --push-ctas 8" ;;
+    nccl_sm16) run $v "--small-allreduce nccl --push-engine sm --push-ctas 16" ;;
+  esac
+done
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_bench_n*_*.json")):

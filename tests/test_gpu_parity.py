@@ -837,65 +837,40 @@ def test_multi_camera_batch_equals_single_camera_calls(cuda_dev):
         assert ok, msg
 
 
-@pytest.mark.parametrize("views,w,h,n,boost", [(1, 160, 96, 6000, 1.2), (3, 250, 130, 5000, 1.2), (1, 64, 48, 20000, 2.0)])
-def test_tile_partitioned_isect_matches_radix_path(cuda_dev, views, w, h, n, boost):
-    """csrc/tilesort.cu (the path rasterization() uses) against the radix path and the oracle: bit-exact."""
+@pytest.mark.parametrize("views,w,h,n,boost", [(1, 160, 96, 6000, 1.2), (3, 250, 130, 5000, 1.2), (1, 64, 48, 20000, 2.0),
+                                               (2, 16, 16, 300, 1.0), (1, 1000, 700, 3000, 0.5)])
+def test_compact_isect_pipeline_matches_radix_path(cuda_dev, views, w, h, n, boost):
+    """The opt-in "compact" intersection pipeline (32-bit camera|tile keys through the radix passes) against the
+    default path and the oracle: bit-exact keys, flatten ids, offsets and tile counts, including equal (tile, depth)
+    keys whose order is the tie rule."""
     from gsplat.cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles,
                                       isect_tiles_and_offsets)
     cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views, spread=1.3, scale_boost=boost)
     means, quats, scales, _, _ = scenes.activate(gs, 3)
     # duplicate some Gaussians so that equal (tile, depth) keys exist and the tie order matters
-    means = torch.cat([means, means[:500]]); quats = torch.cat([quats, quats[:500]]); scales = torch.cat([scales, scales[:500]])
-    m, q, s, v, k = _gpu((means, quats, scales, vm, Ks), cuda_dev)
-    radii, means2d, depths = fully_fused_projection(m, None, q, s, v, k, w, h)[:3]
-    tw, th = math.ceil(w / 16), math.ceil(h / 16)
-    t1, i1, f1 = isect_tiles(means2d, radii, depths, 16, tw, th)
-    o1 = isect_offset_encode(i1, views, tw, th)
-    t2, i2, f2, o2 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th, method="tile")
-    assert torch.equal(t1, t2) and torch.equal(i1, i2) and torch.equal(f1, f2) and torch.equal(o1, o2)
-    r_t, r_i, r_f = O.isect_tiles(means2d.cpu(), radii.cpu(), depths.cpu(), 16, tw, th)
-    assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
-    assert int((i1[1:] == i1[:-1]).sum()) > 100, "the scene must contain equal keys"
-    assert int((o2.flatten()[1:] - o2.flatten()[:-1]).max()) > (600 if n >= 20000 else 50)
-
-
-@pytest.mark.parametrize("views,w,h,n,boost", [(1, 160, 96, 6000, 1.2), (3, 250, 130, 5000, 1.2), (1, 64, 48, 20000, 2.0),
-                                               (2, 16, 16, 300, 1.0), (1, 1000, 700, 3000, 0.5)])
-def test_chunked_counting_sort_isect_matches_radix_path(cuda_dev, views, w, h, n, boost):
-    """csrc/chunksort.cu (opt-in pipeline, measured slower than the radix path) against the radix path and the oracle: bit-exact
-    keys, flatten ids, offsets and tile counts, including equal (tile, depth) keys whose order is the tie rule."""
-    from gsplat.cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles,
-                                      isect_tiles_and_offsets)
-    cfg, gs, vm, Ks = small_scene(n=n, w=w, h=h, views=views, spread=1.3, scale_boost=boost)
-    means, quats, scales, _, _ = scenes.activate(gs, 3)
     means = torch.cat([means, means[:200]]); quats = torch.cat([quats, quats[:200]]); scales = torch.cat([scales, scales[:200]])
     m, q, s, v, k = _gpu((means, quats, scales, vm, Ks), cuda_dev)
     radii, means2d, depths = fully_fused_projection(m, None, q, s, v, k, w, h)[:3]
     tw, th = math.ceil(w / 16), math.ceil(h / 16)
     t1, i1, f1 = isect_tiles(means2d, radii, depths, 16, tw, th)
     o1 = isect_offset_encode(i1, views, tw, th)
-    t2, i2, f2, o2 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th, method="chunk")
-    assert i2.numel() == i1.numel() > 0
-    assert torch.equal(t1, t2) and torch.equal(o1, o2)
-    assert torch.equal(i1, i2) and torch.equal(f1, f2)
-    # the compact (32-bit camera|tile keys) pipeline (opt-in)
+    assert i1.numel() > 0
     t3, i3, f3, o3 = isect_tiles_and_offsets(means2d, radii, depths, 16, tw, th, method="compact")
     assert torch.equal(t1, t3) and torch.equal(o1, o3) and torch.equal(i1, i3) and torch.equal(f1, f3)
     r_t, r_i, r_f = O.isect_tiles(means2d.cpu(), radii.cpu(), depths.cpu(), 16, tw, th)
-    assert torch.equal(i2.cpu(), r_i) and torch.equal(f2.cpu(), r_f)
-    assert torch.equal(o2.cpu(), O.isect_offset_encode(r_i, views, tw, th))
+    assert torch.equal(i3.cpu(), r_i) and torch.equal(f3.cpu(), r_f)
+    assert torch.equal(o3.cpu(), O.isect_offset_encode(r_i, views, tw, th))
     assert int((i1[1:] == i1[:-1]).sum()) > 20, "the scene must contain equal keys"
 
 
-def test_chunked_counting_sort_nothing_visible(cuda_dev):
+def test_compact_isect_pipeline_nothing_visible(cuda_dev):
     from gsplat.cuda._wrapper import isect_tiles_and_offsets
     N = 1000
     means2d = torch.rand(1, N, 2, device=cuda_dev) * 100
     radii = torch.zeros(1, N, 2, device=cuda_dev, dtype=torch.int32)
     depths = torch.rand(1, N, device=cuda_dev)
-    for method in ("chunk", "compact"):
-        t, i, f, o = isect_tiles_and_offsets(means2d, radii, depths, 16, 7, 7, method=method)
-        assert i.numel() == 0 and f.numel() == 0 and int(t.sum()) == 0 and int(o.abs().sum()) == 0 and o.shape == (1, 7, 7)
+    t, i, f, o = isect_tiles_and_offsets(means2d, radii, depths, 16, 7, 7, method="compact")
+    assert i.numel() == 0 and f.numel() == 0 and int(t.sum()) == 0 and int(o.abs().sum()) == 0 and o.shape == (1, 7, 7)
 
 
 def test_forward_two_pixels_per_lane_variant(cuda_dev):
