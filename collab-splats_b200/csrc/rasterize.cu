@@ -192,17 +192,20 @@ struct RasterArgs {
                               //                     warp evaluations, warp evaluations that blended}
 };
 
-template <int DP, int BATCH> struct Smem {
-  float4 q0[2][BATCH], q1[2][BATCH], q2[2][BATCH], q3[2][BATCH];
-  float col[2][BATCH][DP];
+template <int DP, int BATCH, int S = 2> struct Smem {
+  float4 q0[S][BATCH], q1[S][BATCH], q2[S][BATCH], q3[S][BATCH];
+  float col[S][BATCH][DP];
   int ids[2][BATCH];
   int red[8];
+  // S > 2: ring of S staged batches with mbarrier hand-over instead of one CTA barrier per batch (see ring_* below)
+  unsigned long long full[S], empty[S];
+  int done;
 };
 
 // Footprint test of ONE Gaussian (per lane) against the warp's rectangle of pixel centres
 // [rcx - hw, rcx + hw] x [rcy - hh, rcy + hh].  Conservative in both modes (see pack_geom_kernel).
-template <int DP, int BATCH>
-__device__ __forceinline__ bool footprint_hit(const Smem<DP, BATCH>& s, int buf, int j, bool exact, float rcx, float rcy,
+template <int DP, int BATCH, int S>
+__device__ __forceinline__ bool footprint_hit(const Smem<DP, BATCH, S>& s, int buf, int j, bool exact, float rcx, float rcy,
                                               float hw, float hh) {
   const float4 f = s.q0[buf][j];
   const float cx = f.x - rcx, cy = f.y - rcy;   // d = centre - pixel ranges over [cx - hw, cx + hw] x [cy - hh, cy + hh]
@@ -222,8 +225,8 @@ __device__ __forceinline__ bool footprint_hit(const Smem<DP, BATCH>& s, int buf,
 
 // gather one batch (ids already in s.ids[buf]) with 16-byte cp.async copies; consecutive threads copy
 // consecutive 16-byte chunks of one record, so each 64-byte record is one coalesced request
-template <int DP, int BATCH, int NT = RT>
-__device__ __forceinline__ void issue_gather(Smem<DP, BATCH>& s, int buf, int count, const RasterArgs& a, int t) {
+template <int DP, int BATCH, int NT = RT, int S = 2>
+__device__ __forceinline__ void issue_gather(Smem<DP, BATCH, S>& s, int buf, int count, const RasterArgs& a, int t) {
   constexpr int CH = 4 + DP / 4;
   const int total = count * CH;
   for (int i = t; i < total; i += NT) {
@@ -238,6 +241,57 @@ __device__ __forceinline__ void issue_gather(Smem<DP, BATCH>& s, int buf, int co
     }
   }
   rs::cp_async_commit();
+}
+
+// ---- staged-batch ring (S > 2 stages) with mbarrier hand-over.  The CTA barrier per batch couples the tile's four
+// warps (13.8 % / 15.2 % of the backward's / forward's stall samples are warps waiting at it for the slowest one).  In
+// the ring every warp gathers ITS 32 slots of a batch (ids in registers, distributed with shuffles), announces them
+// with cp.async.mbarrier.arrive (the arrival fires when the copies have landed: nobody waits for its own copies), and
+// a stage is refilled once all warps have released it -- so a warp may run up to S - 2 batches ahead of the slowest.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared.b64 st, [%0];\n}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_after_cp_async(unsigned long long* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// waits for the phase; gives up (returns false) when `*done` has reached `all` (every warp of the CTA is finished)
+__device__ __forceinline__ bool mbar_wait_or_done(unsigned long long* bar, unsigned parity, const volatile int* done, int all) {
+  while (!mbar_try_wait(bar, parity))
+    if (*done >= all) return false;
+  return true;
+}
+// this warp's 32 slots of a batch: lane l owns slot 32 warp + l (its flatten id in `my_id`); consecutive lanes copy
+// consecutive 16-byte chunks of a record, as issue_gather does
+template <int DP, int BATCH, int S>
+__device__ __forceinline__ void ring_gather_share(Smem<DP, BATCH, S>& s, int stage, int count, int my_id,
+                                                  const RasterArgs& a, int lane, int warp) {
+  constexpr int CH = 4 + DP / 4;
+#pragma unroll
+  for (int r = 0; r < CH; ++r) {
+    const int c = r * 32 + lane;
+    const int sl = c / CH, ch = c - sl * CH;
+    const int id = __shfl_sync(RS_FULL_MASK, my_id, sl);
+    const int slot = warp * 32 + sl;
+    if (slot < count) {
+      if (ch < 4) {
+        float4* dst = (ch == 0 ? s.q0[stage] : ch == 1 ? s.q1[stage] : ch == 2 ? s.q2[stage] : s.q3[stage]) + slot;
+        rs::cp_async16(dst, a.geom + (size_t)id * 4 + ch);
+      } else {
+        const int row = a.color_per_cam ? id : id % a.N;
+        rs::cp_async16(&s.col[stage][slot][(ch - 4) * 4], a.colors + (size_t)row * DP + (ch - 4) * 4);
+      }
+    }
+  }
+  mbar_arrive_after_cp_async(&s.full[stage]);
 }
 
 struct TileCtx {
@@ -639,11 +693,12 @@ __device__ __forceinline__ float sigma_col(float adx2, float bdx, float c, float
 // count of the (issue-bound) alpha test; 4 warps (128 threads) per tile, 128-Gaussian batches.
 constexpr int RT2 = 128;
 
-template <int DP, int BATCH, bool STATS, int NW>
+template <int DP, int BATCH, bool STATS, int NW, int S = 2>
 __global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArgs a) {
   constexpr int NT = NW * 32, SUB = 4 / NW;   // NW warps per CTA: a CTA covers NW of the tile's four 8x8 blocks
+  static_assert(S == 2 || BATCH == NT, "ring: one slot per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  Smem<DP, BATCH, S>& s = *reinterpret_cast<Smem<DP, BATCH, S>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tile_id = blockIdx.x / SUB;
   const int qd = (blockIdx.x - tile_id * SUB) * NW + warp;   // which 8x8 block of the tile this warp owns
@@ -672,30 +727,59 @@ __global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArg
   int st_contrib[2] = {0, 0}, st_term[2] = {-1, -1}, st_evals = 0, st_blend = 0;  // STATS only
 
   const int nb = (end - start + BATCH - 1) / BATCH;
-  if (nb > 0) {
-    for (int i = t; i < BATCH; i += NT) { const int g = start + i; s.ids[0][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
-    __syncthreads();
-    issue_gather<DP, BATCH, NT>(s, 0, min(BATCH, end - start), a, t);
-    if (nb > 1)
-      for (int i = t; i < BATCH; i += NT) { const int g = start + BATCH + i; s.ids[1][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
-  }
   bool warp_done = !__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f);
-  for (int b = 0; b < nb; ++b) {
-    rs::cp_async_wait_all();
-    if (__syncthreads_count(T[0] != 0.f || T[1] != 0.f) == 0) break;
-    int next_id[BATCH / NT];
-    if (b + 1 < nb) {
-      issue_gather<DP, BATCH, NT>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
-      if (b + 2 < nb) {
+  int ring_id = 0;   // ring: flatten id of this thread's slot in the next batch to gather
+  if constexpr (S == 2) {
+    if (nb > 0) {
+      for (int i = t; i < BATCH; i += NT) { const int g = start + i; s.ids[0][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+      __syncthreads();
+      issue_gather<DP, BATCH, NT>(s, 0, min(BATCH, end - start), a, t);
+      if (nb > 1)
+        for (int i = t; i < BATCH; i += NT) { const int g = start + BATCH + i; s.ids[1][i] = g < end ? __ldg(a.flatten_ids + g) : 0; }
+    }
+  } else {
+    if (t == 0) {
 #pragma unroll
-        for (int r = 0; r < BATCH / NT; ++r) {
-          const int g = start + (b + 2) * BATCH + r * NT + t;
-          next_id[r] = g < end ? __ldg(a.flatten_ids + g) : 0;
+      for (int i = 0; i < S; ++i) { mbar_init(&s.full[i], NT); mbar_init(&s.empty[i], NW); }
+      s.done = 0;
+    }
+    __syncthreads();
+    if (warp_done && lane == 0) atomicAdd(&s.done, 1);
+    if (nb > 0) {
+      ring_id = start + t < end ? __ldg(a.flatten_ids + start + t) : 0;
+      ring_gather_share(s, 0, min(BATCH, end - start), ring_id, a, lane, warp);
+      ring_id = start + BATCH + t < end ? __ldg(a.flatten_ids + start + BATCH + t) : 0;
+    }
+  }
+  for (int b = 0; b < nb; ++b) {
+    int next_id[BATCH / NT];
+    if constexpr (S == 2) {
+      rs::cp_async_wait_all();
+      if (__syncthreads_count(T[0] != 0.f || T[1] != 0.f) == 0) break;
+      if (b + 1 < nb) {
+        issue_gather<DP, BATCH, NT>(s, (b + 1) & 1, min(BATCH, end - (start + (b + 1) * BATCH)), a, t);
+        if (b + 2 < nb) {
+#pragma unroll
+          for (int r = 0; r < BATCH / NT; ++r) {
+            const int g = start + (b + 2) * BATCH + r * NT + t;
+            next_id[r] = g < end ? __ldg(a.flatten_ids + g) : 0;
+          }
         }
       }
+    } else {
+      const volatile int* done = &s.done;
+      if (*done >= NW) break;                                  // every warp of the tile is saturated
+      if (b + 1 < nb) {                                        // refill the stage batch b + 1 - S lived in
+        const int st1 = (b + 1) % S;
+        if (b + 1 >= S && !mbar_wait_or_done(&s.empty[st1], (unsigned)(((b + 1 - S) / S) & 1), done, NW)) break;
+        ring_gather_share(s, st1, min(BATCH, end - (start + (b + 1) * BATCH)), ring_id, a, lane, warp);
+        const int g = start + (b + 2) * BATCH + t;
+        ring_id = g < end ? __ldg(a.flatten_ids + g) : 0;
+      }
+      if (!mbar_wait_or_done(&s.full[b % S], (unsigned)((b / S) & 1), done, NW)) break;
     }
     if (!warp_done) {
-      const int buf = b & 1;
+      const int buf = S == 2 ? (b & 1) : (b % S);
       const int base_idx = start + b * BATCH;
       const int bcount = min(BATCH, end - base_idx);
       for (int g0 = 0; g0 < bcount; g0 += 32) {
@@ -772,12 +856,21 @@ __global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArg
           blend(ja, dxa, dya, ala, oka);
           if (two) blend(jb, dxb, dyb, alb, okb);
         }
-        if (!__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f)) { warp_done = true; break; }
+        if (!__any_sync(RS_FULL_MASK, T[0] != 0.f || T[1] != 0.f)) {
+          warp_done = true;
+          if constexpr (S > 2) { if (lane == 0) atomicAdd(&s.done, 1); }
+          break;
+        }
       }
     }
-    if (b + 2 < nb) {
+    if constexpr (S == 2) {
+      if (b + 2 < nb) {
 #pragma unroll
-      for (int r = 0; r < BATCH / NT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
+        for (int r = 0; r < BATCH / NT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.empty[b % S]);             // this warp is through with the stage
     }
   }
   rs::cp_async_wait_all();
@@ -1150,13 +1243,14 @@ __global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const
 // x-dependent terms and -- the point of the variant -- ONE 16-value warp reduction and ONE 64-byte RED per
 // (warp, Gaussian): their contributions are summed in registers first.  Because dx is common to the two pixels
 // the record's moments factor as dx * (sum over the two pixels), which removes most per-pixel multiplies.
-template <int BATCH, bool ABSGRAD, int MINB, int NW>
+template <int BATCH, bool ABSGRAD, int MINB, int NW, int S = 2>
 __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kernel(const RasterArgs a) {
   constexpr int DP = 4;
   constexpr int NT = NW * 32, SUB = 4 / NW, IPT = BATCH / NT;   // NW warps per CTA; IPT ids per thread and batch
   static_assert(BATCH % NT == 0, "whole ids per thread");
+  static_assert(S == 2 || BATCH == NT, "ring: one slot per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<DP, BATCH>& s = *reinterpret_cast<Smem<DP, BATCH>*>(smem_raw);
+  Smem<DP, BATCH, S>& s = *reinterpret_cast<Smem<DP, BATCH, S>*>(smem_raw);
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int tile_id = blockIdx.x / SUB;
   const int qd = (blockIdx.x - tile_id * SUB) * NW + warp;   // which 8x8 block of the tile this warp owns
@@ -1246,32 +1340,61 @@ __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kerne
   for (int w = 0; w < NW; ++w) blk_last = max(blk_last, s.red[w]);
   const int nb = blk_last >= start ? (blk_last - start) / BATCH + 1 : 0;
 
-  if (nb > 0) {
-    const int bl = nb - 1;
+  int ring_id = 0;   // ring: flatten id of this thread's slot in the next batch to gather
+  if constexpr (S == 2) {
+    if (nb > 0) {
+      const int bl = nb - 1;
 #pragma unroll
-    for (int r = 0; r < IPT; ++r) {
-      const int i = start + bl * BATCH + r * NT + t;
-      s.ids[bl & 1][r * NT + t] = i < end ? __ldg(a.flatten_ids + i) : 0;
+      for (int r = 0; r < IPT; ++r) {
+        const int i = start + bl * BATCH + r * NT + t;
+        s.ids[bl & 1][r * NT + t] = i < end ? __ldg(a.flatten_ids + i) : 0;
+      }
+      __syncthreads();
+      issue_gather<DP, BATCH, NT>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
+      if (bl >= 1) {
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) s.ids[(bl - 1) & 1][r * NT + t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + r * NT + t);
+      }
+    }
+  } else {
+    // ring: iteration it = nb - 1 - b walks the batches back to front; stage = it % S (see ring_gather_share)
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < S; ++i) { mbar_init(&s.full[i], NT); mbar_init(&s.empty[i], NW); }
+      s.done = 0;
     }
     __syncthreads();
-    issue_gather<DP, BATCH, NT>(s, bl & 1, min(BATCH, end - (start + bl * BATCH)), a, t);
-    if (bl >= 1) {
-#pragma unroll
-      for (int r = 0; r < IPT; ++r) s.ids[(bl - 1) & 1][r * NT + t] = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + r * NT + t);
+    if (nb > 0) {
+      const int bl = nb - 1;
+      const int i = start + bl * BATCH + t;
+      ring_id = i < end ? __ldg(a.flatten_ids + i) : 0;
+      ring_gather_share(s, 0, min(BATCH, end - (start + bl * BATCH)), ring_id, a, lane, warp);
+      if (bl >= 1) ring_id = __ldg(a.flatten_ids + start + (bl - 1) * BATCH + t);
     }
   }
   for (int b = nb - 1; b >= 0; --b) {
-    rs::cp_async_wait_all();
-    __syncthreads();
     int next_id[IPT];
-    if (b >= 1) {
-      issue_gather<DP, BATCH, NT>(s, (b - 1) & 1, BATCH, a, t);
-      if (b >= 2) {
+    const int it = nb - 1 - b;
+    if constexpr (S == 2) {
+      rs::cp_async_wait_all();
+      __syncthreads();
+      if (b >= 1) {
+        issue_gather<DP, BATCH, NT>(s, (b - 1) & 1, BATCH, a, t);
+        if (b >= 2) {
 #pragma unroll
-        for (int r = 0; r < IPT; ++r) next_id[r] = __ldg(a.flatten_ids + start + (b - 2) * BATCH + r * NT + t);
+          for (int r = 0; r < IPT; ++r) next_id[r] = __ldg(a.flatten_ids + start + (b - 2) * BATCH + r * NT + t);
+        }
       }
+    } else {
+      if (b >= 1) {                                            // refill the stage iteration it + 1 - S lived in
+        const int st1 = (it + 1) % S;
+        if (it + 1 >= S) mbar_wait_or_done(&s.empty[st1], (unsigned)(((it + 1 - S) / S) & 1), &s.done, 1 << 30);
+        ring_gather_share(s, st1, BATCH, ring_id, a, lane, warp);
+        if (b >= 2) ring_id = __ldg(a.flatten_ids + start + (b - 2) * BATCH + t);
+      }
+      mbar_wait_or_done(&s.full[it % S], (unsigned)((it / S) & 1), &s.done, 1 << 30);
     }
-    const int buf = b & 1;
+    const int buf = S == 2 ? (b & 1) : (it % S);
     const int base_idx = start + b * BATCH;
     const int hi = min(min(BATCH, end - base_idx) - 1, warp_last - base_idx);
     for (int g0 = hi >= 0 ? (hi & ~31) : -32; g0 >= 0; g0 -= 32) {
@@ -1374,9 +1497,14 @@ __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kerne
         }
       }
     }
-    if (b >= 2) {
+    if constexpr (S == 2) {
+      if (b >= 2) {
 #pragma unroll
-      for (int r = 0; r < IPT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
+        for (int r = 0; r < IPT; ++r) s.ids[b & 1][r * NT + t] = next_id[r];
+      }
+    } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.empty[it % S]);            // this warp is through with the stage
     }
   }
   rs::cp_async_wait_all();
@@ -1726,7 +1854,7 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   RS_RETURN_LAST_ERROR();
 }
 // per-call options (include/rade_b200.h); the values must match the header's
-constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_MMA = 0x8;
+constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_MMA = 0x8, F_RING = 0x10;
 static inline int bwd_tune(int flags) { return (flags >> 8) & 0xf; }
 
 template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
@@ -1750,6 +1878,7 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
       // (CTAs of 2 or 1 warps -- half / quarter tiles, no or less barrier coupling -- were measured slower: every CTA
       // gathers the whole tile list, profiles/r02_warps_per_cta_ab.txt)
       if (a.stats) rasterize_fwd2_kernel<DP, B2, true, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);  // counting only
+      else if (a.flags & F_RING) rasterize_fwd2_kernel<DP, B2, false, 4, 3><<<tiles, 128, sizeof(Smem<DP, B2, 3>), st>>>(a);
       else rasterize_fwd2_kernel<DP, B2, false, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
@@ -1804,6 +1933,7 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
       if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4, 4><<<grid, RT2, smem, st>>>(a);
       else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7, 4><<<grid, RT2, smem, st>>>(a);
       else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6, 4><<<grid, RT2, smem, st>>>(a);
+      else if (a.flags & F_RING) rasterize_bwd2_kernel<B2, false, 5, 4, 3><<<grid, RT2, sizeof(Smem<DP, B2, 3>), st>>>(a);
       else rasterize_bwd2_kernel<B2, false, 4, 4><<<grid, RT2, smem, st>>>(a);
       RS_RETURN_LAST_ERROR();
     }

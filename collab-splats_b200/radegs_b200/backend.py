@@ -91,6 +91,7 @@ RS_RASTER_CULL_BBOX = 0x1
 RS_RASTER_ONE_PIXEL = 0x2
 RS_RASTER_NO_COLOR_MMA = 0x4
 RS_RASTER_BWD_MMA = 0x8
+RS_RASTER_RING = 0x10
 
 
 def RS_RASTER_BWD_TUNE(x: int) -> int:

@@ -27,8 +27,9 @@ def step():
 ref = None
 from gsplat.cuda import _wrapper as W
 MMA = be.RS_RASTER_BWD_MMA
-VARIANTS = (("1px", be.RS_RASTER_ONE_PIXEL), ("2px shuffle bwd (default)", 0), ("2px mma bwd", MMA),
-            ("2px mma bwd 128/3", MMA | be.RS_RASTER_BWD_TUNE(1)), ("2px shuffle bwd (default)", 0), ("2px mma bwd", MMA))
+RING = be.RS_RASTER_RING
+VARIANTS = (("2px barrier (default)", 0), ("2px mbarrier ring", RING), ("2px barrier (default)", 0), ("2px mbarrier ring", RING),
+            ("1px", be.RS_RASTER_ONE_PIXEL), ("2px mma bwd", MMA))
 for name, flags in VARIANTS:
     W.RASTER_FLAGS = flags
     for _ in range(3): o, g = step()
