@@ -1854,7 +1854,7 @@ template <int DP, bool STATS> int launch_fwd2(const RasterArgs& a, cudaStream_t 
   RS_RETURN_LAST_ERROR();
 }
 // per-call options (include/rade_b200.h); the values must match the header's
-constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_MMA = 0x8, F_RING = 0x10;
+constexpr int F_CULL_BBOX = 0x1, F_ONE_PIXEL = 0x2, F_NO_COLOR_MMA = 0x4, F_BWD_MMA = 0x8, F_FWD_RING = 0x10, F_BWD_BARRIER = 0x20;
 static inline int bwd_tune(int flags) { return (flags >> 8) & 0xf; }
 
 template <int DP> int launch_fwd_mma(const RasterArgs& a, cudaStream_t st) {
@@ -1878,7 +1878,7 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
       // (CTAs of 2 or 1 warps -- half / quarter tiles, no or less barrier coupling -- were measured slower: every CTA
       // gathers the whole tile list, profiles/r02_warps_per_cta_ab.txt)
       if (a.stats) rasterize_fwd2_kernel<DP, B2, true, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);  // counting only
-      else if (a.flags & F_RING) rasterize_fwd2_kernel<DP, B2, false, 4, 3><<<tiles, 128, sizeof(Smem<DP, B2, 3>), st>>>(a);
+      else if (a.flags & F_FWD_RING) rasterize_fwd2_kernel<DP, B2, false, 4, 3><<<tiles, 128, sizeof(Smem<DP, B2, 3>), st>>>(a);
       else rasterize_fwd2_kernel<DP, B2, false, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);
       RS_RETURN_LAST_ERROR();
     }
@@ -1933,8 +1933,9 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
       if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4, 4><<<grid, RT2, smem, st>>>(a);
       else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7, 4><<<grid, RT2, smem, st>>>(a);
       else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6, 4><<<grid, RT2, smem, st>>>(a);
-      else if (a.flags & F_RING) rasterize_bwd2_kernel<B2, false, 5, 4, 3><<<grid, RT2, sizeof(Smem<DP, B2, 3>), st>>>(a);
-      else rasterize_bwd2_kernel<B2, false, 4, 4><<<grid, RT2, smem, st>>>(a);
+      else if (a.flags & F_BWD_BARRIER) rasterize_bwd2_kernel<B2, false, 4, 4><<<grid, RT2, smem, st>>>(a);
+      else if (tune == 2) rasterize_bwd2_kernel<B2, false, 5, 4, 4><<<grid, RT2, sizeof(Smem<DP, B2, 4>), st>>>(a);
+      else rasterize_bwd2_kernel<B2, false, 5, 4, 3><<<grid, RT2, sizeof(Smem<DP, B2, 3>), st>>>(a);   // default: ring
       RS_RETURN_LAST_ERROR();
     }
   }

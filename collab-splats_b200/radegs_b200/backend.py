@@ -91,7 +91,8 @@ RS_RASTER_CULL_BBOX = 0x1
 RS_RASTER_ONE_PIXEL = 0x2
 RS_RASTER_NO_COLOR_MMA = 0x4
 RS_RASTER_BWD_MMA = 0x8
-RS_RASTER_RING = 0x10
+RS_RASTER_FWD_RING = 0x10
+RS_RASTER_BWD_BARRIER = 0x20
 
 
 def RS_RASTER_BWD_TUNE(x: int) -> int:

@@ -128,8 +128,10 @@ int rs_raster_padded_channels(int D); /* -1 if D > 72: split the channels on the
                                         (vis, v_sigma) against per-pixel constants instead of the shuffle tree: 27 % fewer
                                         instructions, but shared-memory-latency bound -- measured 0.96-0.99 ms vs 0.94 ms at
                                         config 2 (profiles/r02_bwd_mma_ab.txt), so not the default */
-#define RS_RASTER_RING 0x10          /* <= 4 channels, two-pixel kernels: three staged batches handed over with mbarriers
-                                        (cp.async.mbarrier.arrive) instead of one CTA barrier per batch */
+#define RS_RASTER_FWD_RING 0x10      /* <= 4 channels forward: three staged batches handed over with mbarriers
+                                        (cp.async.mbarrier.arrive) instead of one CTA barrier per batch -- the backward's
+                                        default (-1.5 %), measured 6 % slower for the forward */
+#define RS_RASTER_BWD_BARRIER 0x20   /* <= 4 channels backward: the double-buffered CTA-barrier staging instead of the ring */
 #define RS_RASTER_BWD_TUNE(x) (((x) & 0xf) << 8)   /* backward occupancy / batch variant (0 = default), see rasterize.cu */
 int rs_pack_geom(const float* means2d, const float* conics,
                  const float* opacities /* [C*N] if opac_per_cam else [N] */, int opac_per_cam,

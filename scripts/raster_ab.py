@@ -27,8 +27,9 @@ def step():
 ref = None
 from gsplat.cuda import _wrapper as W
 MMA = be.RS_RASTER_BWD_MMA
-RING = be.RS_RASTER_RING
-VARIANTS = (("2px barrier (default)", 0), ("2px mbarrier ring", RING), ("2px barrier (default)", 0), ("2px mbarrier ring", RING),
+FR, BB = be.RS_RASTER_FWD_RING, be.RS_RASTER_BWD_BARRIER
+VARIANTS = (("fwd barrier / bwd ring (default)", 0), ("fwd ring / bwd barrier", FR | BB), ("bwd ring, 4 stages", be.RS_RASTER_BWD_TUNE(2)),
+            ("fwd barrier / bwd ring (default)", 0), ("fwd ring / bwd barrier", FR | BB), ("bwd ring, 4 stages", be.RS_RASTER_BWD_TUNE(2)),
             ("1px", be.RS_RASTER_ONE_PIXEL), ("2px mma bwd", MMA))
 for name, flags in VARIANTS:
     W.RASTER_FLAGS = flags
@@ -40,6 +41,6 @@ for name, flags in VARIANTS:
     if ref is None: ref = (o, g)
     err = max(float((a - b).abs().max()) for a, b in zip(o, ref[0]))
     gerr = max(float((a - b).abs().max() / (b.abs().max() + 1e-30)) for a, b in zip(g, ref[1]))
-    print(f"{name:28s}: sh_fwd {s['rs_sh_colors_fwd'][0] / 10:.4f} sh_bwd {s['rs_sh_colors_bwd'][0] / 10:.4f} emit {s['rs_isect_emit_ordered'][0] / 10:.4f} fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
+    print(f"{name:34s}: sh_fwd {s['rs_sh_colors_fwd'][0] / 10:.4f} sh_bwd {s['rs_sh_colors_bwd'][0] / 10:.4f} emit {s['rs_isect_emit_ordered'][0] / 10:.4f} fwd {s['rs_rasterize_fwd'][0] / 10:.4f} ms  bwd {s['rs_rasterize_bwd'][0] / 10:.4f} ms  "
           f"unpack {s['rs_unpack_geom_grad'][0] / 10:.4f} ms   max|out diff vs first| {err:.2e}  max rel grad diff {gerr:.2e}")
 W.RASTER_FLAGS = 0

@@ -256,12 +256,12 @@ def _raster_inputs(cfg, gs, vm, Ks, D, seed=5, antialiased=True):
 @pytest.fixture
 def raster_variant(request):
     """Selects the compositing variant for <= 4 channels (0: 8x4 pixels per warp, 1: 8x8, two pixels per lane -- the
-    default --, 2: 8x8 with the backward's per-Gaussian reduction on the tensor cores, 3: 8x8 with the mbarrier ring; +10: with the bbox footprint test
+    default --, 2: 8x8 with the backward's per-Gaussian reduction on the tensor cores, 3: 8x8 with the staging schemes swapped (forward mbarrier ring, backward CTA barrier); +10: with the bbox footprint test
     instead of the exact ellipse-vs-rectangle one) through the per-call flags for the duration of a test."""
     from radegs_b200 import backend as be
     from gsplat.cuda import _wrapper as W
     v = request.param % 10
-    flags = {0: be.RS_RASTER_ONE_PIXEL, 1: 0, 2: be.RS_RASTER_BWD_MMA, 3: be.RS_RASTER_RING}[v]
+    flags = {0: be.RS_RASTER_ONE_PIXEL, 1: 0, 2: be.RS_RASTER_BWD_MMA, 3: be.RS_RASTER_FWD_RING | be.RS_RASTER_BWD_BARRIER}[v]
     if request.param >= 10:
         flags |= be.RS_RASTER_CULL_BBOX
     old = W.RASTER_FLAGS
