@@ -31,7 +31,7 @@ for p in (str(ROOT / "collab-splats_b200"), str(ROOT)):
 
 import torch  # noqa: E402
 
-BWD_KERNEL_NAME = "rasterize_bwd2_kernel<128,false,4> (8x8 pixels per warp, two per lane; shuffle-tree reduction)"
+BWD_KERNEL_NAME = "rasterize_bwd2_kernel<128,false,5,4,3> (8x8 pixels per warp, two per lane; mbarrier-ring staging, shuffle-tree reduction)"
 METRIC = "train views/s, rade-gs fwd+bwd (RGB+ED, expected+median depth, normals, depth-normal loss), " \
          "1M Gaussians, 1920x1080"
 UNIT = "views/s"
@@ -338,6 +338,57 @@ class Workload:
         else:
             torch.cuda.current_stream(self.device).wait_stream(self.ar_stream)
         return flat
+
+
+def graph_replay_block(wl, steps, device):
+    """The same resident step with sync-free intersections (gsplat.cuda._wrapper.SYNC_FREE: the intersection count never
+    travels to the host), eagerly and as ONE captured CUDA graph replayed per step.  Verdict r1 #7."""
+    from gsplat.cuda import _wrapper as W
+    out = {}
+    W._ISECT_CAPACITY.clear()
+    W.SYNC_FREE = True
+    try:
+        for _ in range(3):                       # the first one learns the capacity
+            wl.step_resident()
+        torch.cuda.synchronize(device)
+        ref = {k: v.grad.clone() for k, v in wl.params.items()}
+        out["sync_free_eager_ms_per_step"] = time_region(wl.step_resident, steps, 1, device) / steps
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                wl.step_resident()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        wl.zero_grad()
+        wl.last_meta = None                      # a live autograd graph would pin its AccumulateGrad nodes to the stream
+        graph = torch.cuda.CUDAGraph()           # it ran on, and the cross-stream wait would invalidate the capture
+        with torch.cuda.graph(graph, stream=side):
+            loss = wl.forward_loss(wl.viewmat, wl.K, wl.gt)
+            loss.backward()
+            wl.last_meta = None
+        del loss
+        for _ in range(3):
+            graph.replay()
+        out["graph_ms_per_step"] = time_region(graph.replay, steps, 1, device) / steps
+        out["views_per_s"] = 1000.0 * wl.C / out["graph_ms_per_step"]
+        out["isect_overflow"] = bool(W.isect_overflowed(reset=False))
+        worst = 0.0
+        for k, v in wl.params.items():
+            worst = max(worst, float((v.grad - ref[k]).abs().max() / (ref[k].abs().max() + 1e-30)))
+        out["max_rel_grad_diff_vs_eager"] = worst
+        (cap, _), = W._ISECT_CAPACITY.values()
+        out["isect_capacity"] = int(cap)
+        out["what"] = ("fwd + fused loss + bwd of the headline step; intersection buffers sized for 1.25x the count learned "
+                       "on the first step, count read by the kernels from device memory, overflow flag checked after")
+        del graph
+    except Exception as e:  # noqa: BLE001
+        out["error"] = f"{type(e).__name__}: {e}"[:300]
+    finally:
+        W.SYNC_FREE = False
+        W._ISECT_CAPACITY.clear()
+        wl.zero_grad()
+    return out
 
 
 def time_region(fn, steps, world, device):
@@ -950,6 +1001,8 @@ def main():
                                                      int(wl.last_meta["isect_offsets"].numel()), D, peak)
         line["stage_ms"] = {k: round(v, 4) for k, v in sorted(st.items(), key=lambda kv: -kv[1])}
         line["stage_ms"]["sum_of_library_kernels"] = round(sum(st.values()), 4)
+        if world == 1 and not args.no_extras:
+            line["graph_replay"] = graph_replay_block(wl, args.steps, device)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             dt, _, _, _, _, cmeta = cpu_step(args.config, threads)

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(IB)
 isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __restrict__ radii,
                           const float* __restrict__ depths, const int32_t* __restrict__ order,
                           const long long* __restrict__ cum, int C, int N, int tile_w, int tile_h, int tile_bits,
-                          long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids) {
+                          long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids, long long capacity,
+                          int* __restrict__ overflow) {
   constexpr int WARPS = IB / 32;
   __shared__ int s_pref[WARPS][33];
   __shared__ int s_xmin[WARPS][32], s_ymin[WARPS][32], s_w[WARPS][32], s_e[WARPS][32];
@@ -191,6 +192,8 @@ isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __rest
     cum_p = __ldg(cum + p);
     if (tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax))
       cnt = max((xmax - xmin) * (ymax - ymin), 0);
+    // bounded output (capacity-sized buffers, device-side count): the last entry knows the total
+    if (p == total - 1 && overflow && cum_p > capacity) *overflow = 1;
   }
   int incl = cnt;   // inclusive prefix of the counts inside the warp
 #pragma unroll
@@ -221,8 +224,10 @@ isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __rest
     const int w = s_w[warp][lo];
     const int ry = r / w, rx = r - ry * w;
     const unsigned long long tile = (unsigned long long)((s_ymin[warp][lo] + ry) * tile_w + s_xmin[warp][lo] + rx);
-    isect_ids[base + k] = (long long)(s_key[warp][lo] | (tile << 32));
-    flatten_ids[base + k] = s_e[warp][lo];
+    if (base + k < capacity) {
+      isect_ids[base + k] = (long long)(s_key[warp][lo] | (tile << 32));
+      flatten_ids[base + k] = s_e[warp][lo];
+    }
   }
 }
 
@@ -303,9 +308,16 @@ isect_finish32_kernel(const unsigned int* __restrict__ keys32, const int32_t* __
 }
 
 __global__ void __launch_bounds__(IB)
-offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, int n_tiles, int tile_bits, int total,
-                     int32_t* __restrict__ offsets) {
+offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, const long long* __restrict__ n_dev,
+                     int n_tiles, int tile_bits, int total, int32_t* __restrict__ offsets) {
   const long long i = (long long)blockIdx.x * IB + threadIdx.x;
+  if (n_dev) {   // device-side count: M is the capacity the grid was sized for
+    M = min(M, __ldg(n_dev));
+    if (M == 0) {
+      if (i < total) offsets[i] = 0;   // (the grid covers at least `total` threads in this mode)
+      return;
+    }
+  }
   if (i >= M) return;
   const unsigned long long tmask = (1ull << tile_bits) - 1ull;
   unsigned long long k = (unsigned long long)__ldg(isect_ids + i) >> 32;
@@ -408,7 +420,27 @@ extern "C" int rs_isect_emit_ordered(const float* means2d, const int32_t* radii,
   int tile_bits = tile_bits_for((long long)tile_w * tile_h);
   isect_emit_ordered_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
       (const float2*)means2d, (const int2*)radii, depths, order, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
-      flatten_ids);
+      flatten_ids, 0x7fffffffffffffffll, nullptr);
+  RS_RETURN_LAST_ERROR();
+}
+
+// Sync-free form: the output buffers hold `capacity` entries (sized from an earlier step); entries past the capacity
+// are dropped and *overflow (device int, zeroed by the caller once) is raised instead.  The count itself stays on the
+// device: it is the last element of cum_tiles.
+extern "C" int rs_isect_emit_ordered_bounded(const float* means2d, const int32_t* radii, const float* depths,
+                                             const int32_t* order, const long long* cum_tiles, int C, int N, int tile_w,
+                                             int tile_h, long long* isect_ids, int32_t* flatten_ids, long long capacity,
+                                             int32_t* overflow, void* stream) {
+  RsSpan span__("rs_isect_emit_ordered", stream);
+  if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0 || capacity <= 0) return RS_ERR_BAD_ARG;
+  if ((long long)C * N >= (1ll << 31) || capacity >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  if (C == 0 || N == 0) return RS_OK;
+  if (!means2d || !radii || !depths || !order || !cum_tiles || !isect_ids || !flatten_ids || !overflow)
+    return RS_ERR_BAD_ARG;
+  int tile_bits = tile_bits_for((long long)tile_w * tile_h);
+  isect_emit_ordered_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
+      (const float2*)means2d, (const int2*)radii, depths, order, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
+      flatten_ids, capacity, overflow);
   RS_RETURN_LAST_ERROR();
 }
 
@@ -425,8 +457,22 @@ extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, 
     return RS_OK;
   }
   if (!isect_ids) return RS_ERR_BAD_ARG;
-  offset_encode_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, (int)n_tiles,
+  offset_encode_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, nullptr, (int)n_tiles,
                                                                         tile_bits_for(n_tiles), (int)total, offsets);
+  RS_RETURN_LAST_ERROR();
+}
+
+// Sync-free form: the number of sorted keys is min(*n_isects_dev, capacity), read on the device.
+extern "C" int rs_offset_encode_dev(const long long* isect_ids, long long capacity, const long long* n_isects_dev, int C,
+                                    int tile_w, int tile_h, int32_t* offsets, void* stream) {
+  RsSpan span__("rs_offset_encode", stream);
+  if (capacity <= 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets || !isect_ids || !n_isects_dev)
+    return RS_ERR_BAD_ARG;
+  if (capacity >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
+  const long long n_tiles = (long long)tile_w * tile_h, total = n_tiles * C;
+  const long long threads = capacity > total ? capacity : total;
+  offset_encode_kernel<<<rs_div_up(threads, IB), IB, 0, (cudaStream_t)stream>>>(
+      isect_ids, capacity, n_isects_dev, (int)n_tiles, tile_bits_for(n_tiles), (int)total, offsets);
   RS_RETURN_LAST_ERROR();
 }
 

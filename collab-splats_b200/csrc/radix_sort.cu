@@ -37,8 +37,10 @@ struct PassInfo {
 
 template <typename K>
 __global__ void __launch_bounds__(ST)
-radix_hist_kernel(const K* __restrict__ keys, long long M, PassInfo pi, u32* __restrict__ ghist) {
+radix_hist_kernel(const K* __restrict__ keys, long long M, const long long* __restrict__ n_dev, PassInfo pi,
+                  u32* __restrict__ ghist) {
   __shared__ u32 sh[MAX_PASSES * RADIX];
+  if (n_dev) M = min(M, __ldg(n_dev));   // device-side count: M is the capacity the grid was sized for
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += ST) sh[i] = 0;
   __syncthreads();
   const long long stride = (long long)gridDim.x * ST;
@@ -74,8 +76,8 @@ __device__ __forceinline__ u32 block_inclusive_scan(u32 v, u32* s_warp, int lane
 template <typename K, int SI, int LB_WINDOW>
 __global__ void __launch_bounds__(ST, (SI == 8 ? 4 : 2))
 radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
-                     u32* __restrict__ vout, int M, int shift, u32 mask, const u32* __restrict__ ghist,
-                     volatile u32* status, u32* ticket) {
+                     u32* __restrict__ vout, int M, const long long* __restrict__ n_dev, int shift, u32 mask,
+                     const u32* __restrict__ ghist, volatile u32* status, u32* ticket) {
   __shared__ u32 s_cnt[SWARPS][RADIX];
   __shared__ u32 s_bin_start[RADIX];
   __shared__ int s_gbase[RADIX];
@@ -90,6 +92,10 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
   __syncthreads();
   const int tile = (int)s_tile;
   const int tile_base = tile * STILE;
+  if (n_dev) {   // device-side count: tiles past it leave at once (tickets are handed out in order: no valid tile waits for them)
+    M = (int)min((long long)M, __ldg(n_dev));
+    if (tile_base >= M) return;
+  }
   const int n_valid = min(STILE, M - tile_base);
 
   // ---- load (warp-contiguous, index order = (round, lane) inside each warp's 512-pair slice)
@@ -215,7 +221,7 @@ extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int en
 
 template <typename K>
 static int sort_pairs_impl(K* ka, u32* va, K* kb, u32* vb, bool iota_vals, long long M, int begin_bit, int end_bit,
-                           void* temp, long long temp_bytes, void* stream) {
+                           void* temp, long long temp_bytes, void* stream, const long long* n_dev = nullptr) {
   if (M < 0 || begin_bit < 0 || end_bit > (int)(8 * sizeof(K))) return RS_ERR_BAD_ARG;
   if (M >= (1ll << 30)) return RS_ERR_UNSUPPORTED;  // look-back words carry 30-bit counts
   if (M == 0 || end_bit <= begin_bit) return 1;
@@ -247,11 +253,11 @@ static int sort_pairs_impl(K* ka, u32* va, K* kb, u32* vb, bool iota_vals, long 
   u32* status = (u32*)((char*)temp + MAX_PASSES * RADIX * 4 + 256);
   int hist_blocks = (int)(nblocks < 148 * 8 ? nblocks : 148 * 8);
   const long long status_stride = sort_blocks(M, 8) * RADIX;
-  radix_hist_kernel<K><<<hist_blocks, ST, 0, st>>>(ka, M, pi, ghist);
+  radix_hist_kernel<K><<<hist_blocks, ST, 0, st>>>(ka, M, n_dev, pi, ghist);
   for (int p = 0; p < npass; ++p) {
     const u32* vin = (p == 0 && iota_vals) ? nullptr : va;
 #define RS_LAUNCH_SCATTER(SI, LBW)                                                                              \
-  radix_scatter_kernel<K, SI, LBW><<<(unsigned)nblocks, ST, 0, st>>>(ka, vin, kb, vb, (int)M, pi.shift[p],      \
+  radix_scatter_kernel<K, SI, LBW><<<(unsigned)nblocks, ST, 0, st>>>(ka, vin, kb, vb, (int)M, n_dev, pi.shift[p], \
                                                                      pi.mask[p], ghist + p * RADIX,             \
                                                                      status + (size_t)p * status_stride, tickets + p)
     if (items == 16) { if (g_sort_window == 16) RS_LAUNCH_SCATTER(16, 16); else if (g_sort_window == 8) RS_LAUNCH_SCATTER(16, 8); else RS_LAUNCH_SCATTER(16, 4); }
@@ -273,6 +279,16 @@ extern "C" int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys
   RsSpan span__("rs_sort_pairs", stream);
   return sort_pairs_impl<u64>((u64*)keys_a, (u32*)vals_a, (u64*)keys_b, (u32*)vals_b, false, M, begin_bit, end_bit,
                               temp, temp_bytes, stream);
+}
+
+// Sync-free form: sorts the first min(*n_pairs_dev, capacity) pairs; buffers, temp and grids are sized for `capacity`.
+extern "C" int rs_sort_pairs_dev(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b,
+                                 long long capacity, const long long* n_pairs_dev, int begin_bit, int end_bit, void* temp,
+                                 long long temp_bytes, void* stream) {
+  RsSpan span__("rs_sort_pairs", stream);
+  if (!n_pairs_dev || capacity <= 0) return RS_ERR_BAD_ARG;
+  return sort_pairs_impl<u64>((u64*)keys_a, (u32*)vals_a, (u64*)keys_b, (u32*)vals_b, false, capacity, begin_bit,
+                              end_bit, temp, temp_bytes, stream, n_pairs_dev);
 }
 
 // Same for 32-bit keys (the depth keys of the presorted intersection path).  vals_a's CONTENT is not read: the

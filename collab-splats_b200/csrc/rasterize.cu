@@ -174,6 +174,7 @@ struct RasterArgs {
   const int* offsets;        // [C*tile_h*tile_w]
   const int* flatten_ids;    // [M]
   int M;
+  const long long* M_dev;    // device-side count (sync-free callers; M is then the buffers' capacity), or null
   // forward outputs == backward saved tensors
   float* out_colors;   // [C,H,W,D]
   float* out_alphas;   // [C,H,W]
@@ -294,6 +295,11 @@ __device__ __forceinline__ void ring_gather_share(Smem<DP, BATCH, S>& s, int sta
   mbar_arrive_after_cp_async(&s.full[stage]);
 }
 
+// end of the last tile's list: the number of intersections, read from the device when the caller never learned it
+__device__ __forceinline__ int list_end(const RasterArgs& a) {
+  return a.M_dev ? (int)min((long long)a.M, __ldg(a.M_dev)) : a.M;
+}
+
 struct TileCtx {
   int cam, start, end, x0, y0, pxi, pyi;
   bool inside;
@@ -308,7 +314,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const RasterArgs& a, int lane, int w
   const int tl = tile_id - c.cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   c.start = __ldg(a.offsets + tile_id);
-  c.end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  c.end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
   c.x0 = txi * RS_TILE + (warp & 1) * 8;
   c.y0 = tyi * RS_TILE + (warp >> 1) * 4;
   c.pxi = c.x0 + (lane & 7);
@@ -707,7 +713,7 @@ __global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArg
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
   const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const int pyi[2] = {y0 + (lane >> 3), y0 + (lane >> 3) + 4};
@@ -1259,7 +1265,7 @@ __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kerne
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
   const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const float px = pxi + 0.5f;
@@ -1669,7 +1675,7 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : a.M;
+  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
   const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const float px = pxi + 0.5f;
@@ -2018,7 +2024,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
                                 const int32_t* flatten_ids, long long M, float* out_colors, float* out_alphas,
                                 float* out_expected_depths, float* out_median_depths, float* out_normals,
                                 float* out_transmittance, int32_t* last_ids, int32_t* median_ids, int flags,
-                                unsigned long long* stats, void* stream) {
+                                unsigned long long* stats, const long long* n_isects_dev, void* stream) {
   RsSpan span__("rs_rasterize_fwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
@@ -2032,6 +2038,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
   a.stats = stats;
+  a.M_dev = n_isects_dev;
   if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
     return RS_ERR_BAD_ARG;
   if (ed_channel >= D) return RS_ERR_BAD_ARG;
@@ -2053,7 +2060,8 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
                                 const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
                                 const float* v_colors, const float* v_alphas, const float* v_expected_depths,
                                 const float* v_median_depths, const float* v_normals, float* geom_grad,
-                                float* color_grad, float* abs_grad, int flags, void* stream) {
+                                float* color_grad, float* abs_grad, int flags, const long long* n_isects_dev,
+                                void* stream) {
   RsSpan span__("rs_rasterize_bwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
@@ -2068,6 +2076,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
   a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;
   a.v_colors = v_colors; a.v_alphas = v_alphas; a.v_dexp = v_expected_depths; a.v_dmed = v_median_depths;
   a.v_normals = v_normals; a.geom_grad = geom_grad; a.color_grad = color_grad; a.abs_grad = abs_grad;
+  a.M_dev = n_isects_dev;
   const int DP = padded_channels(D);
   if (!check_common(a) || !v_colors || !v_alphas || !v_expected_depths || !v_median_depths || !v_normals ||
       !geom_grad || (DP > 4 && !color_grad) || (ed_channel >= 0 && !out_colors) || ed_channel >= D)

@@ -39,6 +39,29 @@ ISECT_PIPELINE = "radix"
 # with its saved tensors, so the backward of a render always uses the flags its forward used.
 RASTER_FLAGS = int(os.environ.get("RADE_RASTER_FLAGS", "0"), 0)   # (the environment variable only seeds the default)
 RASTER_STATS = None
+# Sync-free intersections (opt-in, for training loops and CUDA-graph capture): when True, `rasterization()` learns the
+# number of intersections of a (device, C, N, tile grid) problem on its FIRST call (one device->host read, as always) and
+# from then on sizes `isect_ids` / `flatten_ids` for ISECT_HEADROOM x that count and never reads the count back: the
+# kernels take it from device memory.  `meta["isect_ids"]` / `meta["flatten_ids"]` then have the CAPACITY's length,
+# `meta["n_isects"]` is a device scalar and `meta["isect_overflow"]` a device flag that is raised (check it off the hot
+# path with `isect_overflowed()`) if a step ever produced more intersections than the capacity.
+SYNC_FREE = False
+ISECT_HEADROOM = 1.25
+_ISECT_CAPACITY = {}      # (device index, C, N, tile_w, tile_h) -> [capacity, overflow flag tensor]
+
+
+def isect_overflowed(reset: bool = True) -> bool:
+    """True if any sync-free call since the last check dropped intersections (device->host read: off the hot path).
+    The capacities of the problems that overflowed are forgotten, so their next call re-learns them."""
+    bad = False
+    for key, (cap, flag) in list(_ISECT_CAPACITY.items()):
+        if int(flag.item()) != 0:
+            bad = True
+            if reset:
+                del _ISECT_CAPACITY[key]
+    return bad
+
+
 # Set by radegs_b200.multiview.ShGradExchange while a camera-sharded multi-GPU step runs: the backward of the
 # fused SH colours then publishes per-camera colour gradients instead of producing the coefficient gradient.
 SH_GRAD_SINK = None
@@ -375,6 +398,71 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
 
 
 @torch.no_grad()
+def isect_tiles_and_offsets_sync_free(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int):
+    """`isect_tiles_and_offsets` without the device->host read of the intersection count (see SYNC_FREE).
+    -> tiles_per_gauss, isect_ids [capacity], flatten_ids [capacity], isect_offsets, n_isects (device i64 scalar),
+    overflow (device i32 flag); None if the capacity of this problem has not been learned yet."""
+    lib = _be.load()
+    C, N = depths.shape
+    dev = means2d.device
+    key = (dev.index, C, N, tile_width, tile_height)
+    if key not in _ISECT_CAPACITY or C * N == 0:
+        return None
+    cap, overflow = _ISECT_CAPACITY[key]
+    means2d, depths = _c(means2d), _c(depths)
+    radii = _c(radii, torch.int32)
+    n_elems = C * N
+    tiles = torch.empty(C, N, device=dev, dtype=torch.int32)
+    cum = torch.empty(n_elems, device=dev, dtype=torch.int64)
+    tile_bits = lib.rs_tile_bits(tile_width, tile_height)
+    end_bit = 32 + tile_bits + max(int(C - 1).bit_length(), 0)
+    offsets = torch.empty(C, tile_height, tile_width, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        st = _be.stream_ptr(dev)
+        _be.check(lib.rs_isect_count(_be.ptr(means2d), _be.ptr(radii), n_elems, tile_width, tile_height,
+                                     _be.ptr(tiles), st), "rs_isect_count")
+        dkeys = depths.clone().view(torch.int32)          # the sort clobbers its key buffers
+        dkeys_b = torch.empty_like(dkeys)
+        ord_a = torch.empty(n_elems, device=dev, dtype=torch.int32)
+        ord_b = torch.empty_like(ord_a)
+        sb = lib.rs_sort_pairs_temp_bytes(n_elems, 0, 32)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        where = _be.check(lib.rs_argsort_u32(_be.ptr(dkeys), _be.ptr(ord_a), _be.ptr(dkeys_b), _be.ptr(ord_b),
+                                             n_elems, 0, 32, _be.ptr(stemp), sb, st), "rs_argsort_u32")
+        order = ord_b if where == 0 else ord_a
+        tb = lib.rs_cumsum_temp_bytes(n_elems)
+        temp = torch.empty(tb, device=dev, dtype=torch.uint8)
+        _be.check(lib.rs_cumsum_gather_i32_i64(_be.ptr(tiles), _be.ptr(order), _be.ptr(cum), n_elems,
+                                               _be.ptr(temp), tb, st), "rs_cumsum_gather_i32_i64")
+        n_isects = cum[n_elems - 1]                        # stays on the device
+        ids_a = torch.empty(cap, device=dev, dtype=torch.int64)
+        flat_a = torch.empty(cap, device=dev, dtype=torch.int32)
+        ids_b, flat_b = torch.empty_like(ids_a), torch.empty_like(flat_a)
+        _be.check(lib.rs_isect_emit_ordered_bounded(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), _be.ptr(order),
+                                                    _be.ptr(cum), C, N, tile_width, tile_height, _be.ptr(ids_a),
+                                                    _be.ptr(flat_a), cap, _be.ptr(overflow), st),
+                  "rs_isect_emit_ordered_bounded")
+        sb = lib.rs_sort_pairs_temp_bytes(cap, 32, end_bit)
+        stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
+        where = _be.check(lib.rs_sort_pairs_dev(_be.ptr(ids_a), _be.ptr(flat_a), _be.ptr(ids_b), _be.ptr(flat_b), cap,
+                                                _be.ptr(n_isects), 32, end_bit, _be.ptr(stemp), sb, st),
+                          "rs_sort_pairs_dev")
+        ids, flat = (ids_b, flat_b) if where == 0 else (ids_a, flat_a)
+        _be.check(lib.rs_offset_encode_dev(_be.ptr(ids), cap, _be.ptr(n_isects), C, tile_width, tile_height,
+                                           _be.ptr(offsets), st), "rs_offset_encode_dev")
+    return tiles, ids, flat, offsets, n_isects, overflow
+
+
+def isect_learn_capacity(device, C: int, N: int, tile_width: int, tile_height: int, n_isects: int):
+    """Records the capacity for later sync-free calls of this problem (called by rasterization() after a synchronising
+    call while SYNC_FREE is on)."""
+    key = (device.index, C, N, tile_width, tile_height)
+    cap = max(int(n_isects * ISECT_HEADROOM) + 4096, 4096)
+    cap = (cap + 2047) // 2048 * 2048
+    _ISECT_CAPACITY[key] = [cap, torch.zeros(1, device=device, dtype=torch.int32)]
+
+
+@torch.no_grad()
 def isect_offset_encode(isect_ids: Tensor, n_cameras: int, tile_width: int, tile_height: int) -> Tensor:
     """Same call as gsplat ``isect_offset_encode``: -> offsets [C, tile_height, tile_width] i32."""
     lib = _be.load()
@@ -450,7 +538,7 @@ def sh_colors(degree: int, means: Tensor, coeffs: Tensor, viewmats: Tensor, radi
 class _RasterizeToPixels(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means2d, conics, colors, opacities, compensations, ray_ts, ray_planes, normals, backgrounds,
-                Ks, width, height, isect_offsets, flatten_ids, absgrad, ed_channel):
+                Ks, width, height, isect_offsets, flatten_ids, absgrad, ed_channel, n_isects=None):
         lib = _be.load()
         C, N = means2d.shape[:2]
         dev = means2d.device
@@ -489,9 +577,10 @@ class _RasterizeToPixels(torch.autograd.Function):
                 _be.ptr(geom), _be.ptr(colors_p), int(color_per_cam), D, ed_channel, _be.ptr(backgrounds), _be.ptr(Ks),
                 C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
                 _be.ptr(out_colors), _be.ptr(out_alphas), _be.ptr(out_dexp), _be.ptr(out_dmed), _be.ptr(out_normals),
-                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), flags, _be.ptr(stats), st), "rs_rasterize_fwd")
+                _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), flags, _be.ptr(stats), _be.ptr(n_isects), st),
+                "rs_rasterize_fwd")
         ctx.save_for_backward(geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids,
-                              median_ids, opacities, compensations, out_colors if ed_channel >= 0 else None)
+                              median_ids, opacities, compensations, out_colors if ed_channel >= 0 else None, n_isects)
         ctx.cfg = (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad,
                    ed_channel, colors.shape, flags)
         ctx.means2d_ref = means2d if absgrad else None
@@ -503,7 +592,7 @@ class _RasterizeToPixels(torch.autograd.Function):
     def backward(ctx, v_colors, v_alphas, v_dexp, v_dmed, v_normals, _v_last, _v_med):
         lib = _be.load()
         (geom, colors_p, backgrounds, Ks, isect_offsets, flatten_ids, out_T, last_ids, median_ids, opacities,
-         compensations, out_colors) = ctx.saved_tensors
+         compensations, out_colors, n_isects) = ctx.saved_tensors
         (C, N, D, DP, color_per_cam, opac_per_cam, rows, width, height, tile_w, tile_h, M, absgrad, ed_channel,
          colors_shape, flags) = ctx.cfg
         dev = geom.device
@@ -536,7 +625,7 @@ class _RasterizeToPixels(torch.autograd.Function):
                 C, N, width, height, tile_w, tile_h, _be.ptr(isect_offsets), _be.ptr(flatten_ids) if M else None, M,
                 _be.ptr(out_colors), _be.ptr(out_T), _be.ptr(last_ids), _be.ptr(median_ids), _be.ptr(v_colors),
                 _be.ptr(v_alphas), _be.ptr(v_dexp), _be.ptr(v_dmed), _be.ptr(v_normals), _be.ptr(geom_grad),
-                _be.ptr(color_grad), _be.ptr(abs_grad), flags, st), "rs_rasterize_bwd")
+                _be.ptr(color_grad), _be.ptr(abs_grad), flags, _be.ptr(n_isects), st), "rs_rasterize_bwd")
             _be.check(lib.rs_unpack_geom_grad(
                 _be.ptr(geom_grad), _be.ptr(geom), _be.ptr(abs_grad), C, N, _be.ptr(opacities), int(opac_per_cam),
                 _be.ptr(compensations), _be.ptr(v_means2d), _be.ptr(v_abs), _be.ptr(v_conics), _be.ptr(v_opac),
@@ -557,7 +646,7 @@ class _RasterizeToPixels(torch.autograd.Function):
         if backgrounds is not None and ctx.needs_input_grad[8]:
             v_bg = (v_colors * out_T[..., None]).sum(dim=(1, 2))
         return (v_means2d, v_conics, v_col, v_opac, v_comps, v_ray_ts, v_ray_planes, v_nrm, v_bg, None, None, None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def rasterize_to_pixels(
@@ -581,6 +670,8 @@ def rasterize_to_pixels(
     return_ids: bool = False,
     compensations: Optional[Tensor] = None,  # [C,N]    fused: effective opacity = opacities * compensations
     ed_channel: int = -1,                    # fused "ED": that output channel is divided by max(alpha, 1e-10)
+    n_isects: Optional[Tensor] = None,       # device i64 scalar: the number of valid entries of flatten_ids (sync-free
+                                             # callers, whose buffers are capacity-sized); None = all of them
 ):
     """gsplat ``rasterize_to_pixels`` + the RaDe outputs.  Returns ``(colors [C,H,W,D], alphas [C,H,W,1])``
     or, when the RaDe inputs are given, ``(colors, alphas, expected_depths [C,H,W,1], median_depths
@@ -609,7 +700,7 @@ def rasterize_to_pixels(
     out = _RasterizeToPixels.apply(_c(means2d) if not absgrad else means2d, _c(conics), _c(colors), _c(opacities),
                                    _c(compensations), _c(ray_ts), _c(ray_planes), _c(normals), _c(backgrounds),
                                    _c(Ks), int(image_width), int(image_height), _c(isect_offsets, torch.int32),
-                                   _c(flatten_ids, torch.int32), bool(absgrad), int(ed_channel))
+                                   _c(flatten_ids, torch.int32), bool(absgrad), int(ed_channel), n_isects)
     cols, alphas, dexp, dmed, nrm, last_ids, median_ids = out
     res = (cols, alphas, dexp, dmed, nrm) if rade else (cols, alphas)
     if return_ids:

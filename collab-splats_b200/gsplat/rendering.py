@@ -16,6 +16,7 @@ from typing import Dict, Optional, Tuple
 import torch
 from torch import Tensor
 
+from .cuda import _wrapper as _W
 from .cuda._wrapper import (fully_fused_projection, isect_offset_encode, isect_tiles, isect_tiles_and_offsets,
                             rasterize_to_pixels, sh_colors, spherical_harmonics)
 
@@ -122,8 +123,15 @@ def rasterization(
     # ---- tile intersection, sort, offsets
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
-        means2d, radii, depths, tile_size, tile_width, tile_height)
+    n_isects = overflow = None
+    sf = _W.isect_tiles_and_offsets_sync_free(means2d, radii, depths, tile_width, tile_height) if _W.SYNC_FREE else None
+    if sf is not None:      # no device->host read: capacity-sized lists, the count stays on the device
+        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets, n_isects, overflow = sf
+    else:
+        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
+            means2d, radii, depths, tile_size, tile_width, tile_height)
+        if _W.SYNC_FREE:    # first call of this problem: remember how many intersections it has
+            _W.isect_learn_capacity(means2d.device, C, N, tile_width, tile_height, flatten_ids.numel())
 
     # ---- compositing (one pass up to 72 channels; wider colours are split, geometry comes from the first pass).
     # The "ED" normalisation (depth channel / alpha) runs in the kernel epilogue.
@@ -133,7 +141,7 @@ def rasterization(
         render_colors, render_alphas, exp_d, med_d, nrm = rasterize_to_pixels(
             means2d, conics, cols, opacities, width, height, tile_size, isect_offsets, flatten_ids,
             backgrounds=backgrounds, absgrad=absgrad, ray_ts=ray_ts, ray_planes=ray_planes, normals=normals, Ks=Ks,
-            compensations=compensations, ed_channel=(D - 1) if ed else -1)
+            compensations=compensations, ed_channel=(D - 1) if ed else -1, n_isects=n_isects)
     else:
         chunk = min(max(int(channel_chunk), 1), 64) if channel_chunk > 32 else 64   # (upstream's default 32 -> one 64-wide pass)
         if absgrad and hasattr(means2d, "absgrad"):
@@ -146,7 +154,7 @@ def rasterization(
             out = rasterize_to_pixels(means2d, conics, cols[..., k0:k1], opacities, width, height, tile_size,
                                       isect_offsets, flatten_ids, backgrounds=bg, absgrad=absgrad, ray_ts=ray_ts,
                                       ray_planes=ray_planes, normals=normals, Ks=Ks, compensations=compensations,
-                                      ed_channel=(k1 - k0 - 1) if (ed and k1 == D) else -1)
+                                      ed_channel=(k1 - k0 - 1) if (ed and k1 == D) else -1, n_isects=n_isects)
             parts.append(out[0])
             if k0 == 0:
                 render_alphas, exp_d, med_d, nrm = out[1:]
@@ -160,6 +168,7 @@ def rasterization(
         "tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
         "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
         "height": height, "tile_size": tile_size, "n_cameras": C,
+        "n_isects": n_isects if n_isects is not None else flatten_ids.numel(), "isect_overflow": overflow,
     }
     if return_depth_normal:
         return render_colors, render_alphas, exp_d, med_d, nrm, meta

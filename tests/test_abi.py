@@ -61,7 +61,7 @@ def test_argument_validation_before_any_launch(lib):
     assert lib.rs_sort_pairs(null, null, null, null, 1 << 31, 0, 46, null, 0, null) == -3
     assert lib.rs_isect_count(null, null, 5, 4, 4, null, null) == -1
     assert lib.rs_rasterize_fwd(null, null, 0, 3, -1, null, null, 1, 1, 16, 16, 1, 1, null, null, 0, null, null, null,
-                                null, null, null, null, null, 0, null, null) == -1
+                                null, null, null, null, null, 0, null, null, null) == -1
     assert lib.rs_sh_colors_fwd(4, 25, 1, 10, null, null, null, null, null, null, null) == -1   # degree > 3
     # zero-sized problems are fine
     assert lib.rs_project_fwd(null, null, null, null, null, 1, 0, 64, 64, 0.3, 0.01, 1e10, 0.0, 0, null, null, null,
