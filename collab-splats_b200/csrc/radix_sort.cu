@@ -18,10 +18,8 @@ typedef unsigned int u32;
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int ST = 256;            // threads per block
-// items per thread: 8 (64 registers, 4 CTAs/SM, 2048-pair tiles) or 16 (98 registers, 2 CTAs/SM, 4096-pair tiles);
-// selectable at run time (rs_sort_set_items) so both can be measured on the same box
-static int g_sort_items = 8;
-static int g_sort_window = 4;      // look-back polling window (4, 8 or 16 predecessors per round trip)
+constexpr int SITEMS = 8;          // pairs per thread: 64 registers, 4 CTAs/SM, 2048-pair tiles (16: 98 registers, slower)
+constexpr int LBW = 8;             // look-back polling window: predecessors polled per round trip
 constexpr int SWARPS = ST / 32;
 constexpr int MAX_PASSES = 8;
 #define LB_AGG (1u << 30)
@@ -72,12 +70,21 @@ __device__ __forceinline__ u32 block_inclusive_scan(u32 v, u32* s_warp, int lane
   return v + off;
 }
 
-// K = u64 (tile|depth keys) or u32 (depth keys of the presorted path); vin == nullptr: the value of pair i is i
+// K = u64 (tile|depth keys) or u32 (depth keys of the presorted path); vin == nullptr: the value of pair i is i.
+// Round 2 shortened the per-tile dependency chain of the round-1 kernel (-4 %, profiles/r02_sort_ab.txt):
+//  * ranking: all match.any of a thread's items are issued back to back, the digit leaders then bump the warp's counter
+//    row with one shared-memory atomic each (program order within the warp keeps the rounds ordered) and the bases come
+//    back with one shuffle per item: three pipelined groups instead of 8 dependent match -> LDS -> STS -> SHFL chains;
+//  * the global digit bases ride in the look-back: tile 0 alone scans the global histogram and publishes
+//    base + count as its inclusive prefix, so every other tile gets base + predecessors from the look-back sum
+//    (one block scan and two barriers fewer per tile);
+//  * keys and values are reordered through separate shared arrays in the same phase (one barrier pair fewer, key and
+//    value stores of a row issued together).
 template <typename K, int SI, int LB_WINDOW>
-__global__ void __launch_bounds__(ST, (SI == 8 ? 4 : 2))
+__global__ void __launch_bounds__(ST, 4)
 radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* __restrict__ kout,
-                     u32* __restrict__ vout, int M, const long long* __restrict__ n_dev, int shift, u32 mask,
-                     const u32* __restrict__ ghist, volatile u32* status, u32* ticket) {
+                      u32* __restrict__ vout, int M, const long long* __restrict__ n_dev, int shift, u32 mask,
+                      const u32* __restrict__ ghist, volatile u32* status, u32* ticket) {
   __shared__ u32 s_cnt[SWARPS][RADIX];
   __shared__ u32 s_bin_start[RADIX];
   __shared__ int s_gbase[RADIX];
@@ -85,6 +92,7 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
   __shared__ u32 s_tile;
   constexpr int STILE = ST * SI;
   __shared__ __align__(16) K s_keys[STILE];
+  __shared__ __align__(16) u32 s_vals[STILE];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
@@ -92,13 +100,12 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
   __syncthreads();
   const int tile = (int)s_tile;
   const int tile_base = tile * STILE;
-  if (n_dev) {   // device-side count: tiles past it leave at once (tickets are handed out in order: no valid tile waits for them)
+  if (n_dev) {
     M = (int)min((long long)M, __ldg(n_dev));
     if (tile_base >= M) return;
   }
   const int n_valid = min(STILE, M - tile_base);
 
-  // ---- load (warp-contiguous, index order = (round, lane) inside each warp's 512-pair slice)
   K key[SI];
   u32 val[SI];
 #pragma unroll
@@ -109,22 +116,19 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
     val[r] = ok ? (vin ? __ldg(vin + tile_base + i) : (u32)(tile_base + i)) : 0u;
   }
   // ---- warp-local stable ranks
-  u32 pos[SI];
+  u32 pos[SI], peers[SI];
   const u32 lt = rs::lanemask_lt();
 #pragma unroll
+  for (int r = 0; r < SI; ++r) peers[r] = __match_any_sync(RS_FULL_MASK, (u32)((key[r] >> shift) & mask));
+#pragma unroll
   for (int r = 0; r < SI; ++r) {
-    const u32 d = (u32)((key[r] >> shift) & mask);
-    const u32 peers = __match_any_sync(RS_FULL_MASK, d);
-    const int leader = __ffs(peers) - 1;
-    u32 old = 0;
-    if (lane == leader) {
-      old = s_cnt[warp][d];
-      s_cnt[warp][d] = old + __popc(peers);
-    }
-    old = __shfl_sync(RS_FULL_MASK, old, leader);
-    pos[r] = old + __popc(peers & lt);
-    __syncwarp();
+    pos[r] = 0;
+    if ((peers[r] & lt) == 0u)   // lowest lane of the digit group
+      pos[r] = atomicAdd(&s_cnt[warp][(u32)((key[r] >> shift) & mask)], (u32)__popc(peers[r]));
   }
+#pragma unroll
+  for (int r = 0; r < SI; ++r)
+    pos[r] = __shfl_sync(RS_FULL_MASK, pos[r], __ffs(peers[r]) - 1) + __popc(peers[r] & lt);
   __syncthreads();
   // ---- per digit (thread t == digit): prefix over warps, block count
   u32 bcount = 0;
@@ -134,34 +138,33 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
     s_cnt[w][t] = bcount;
     bcount += c;
   }
-  // ---- publish the block's digit count early, so successors can aggregate it while this block reorders
   volatile u32* my_status = status + (size_t)tile * RADIX + t;
-  *my_status = (tile == 0 ? LB_PREFIX : LB_AGG) | bcount;
-  const u32 gh = __ldg(ghist + t);
+  u32 excl_prev = 0;
+  if (tile == 0) {   // block-uniform: the global base of every digit, published as part of the first inclusive prefix
+    const u32 gh = __ldg(ghist + t);
+    excl_prev = block_inclusive_scan(gh, s_warp, lane, warp) - gh;
+    *my_status = LB_PREFIX | (excl_prev + bcount);
+  } else {
+    *my_status = LB_AGG | bcount;
+  }
   const u32 bin_incl = block_inclusive_scan(bcount, s_warp, lane, warp);
-  const u32 gh_incl = block_inclusive_scan(gh, s_warp, lane, warp);
   s_bin_start[t] = bin_incl - bcount;
   __syncthreads();
-  // ---- reorder keys through shared memory (needs only block-local offsets) BEFORE the look-back, so that the
-  //      predecessors have had time to publish their inclusive prefixes and the look-back chains stay short
 #pragma unroll
   for (int r = 0; r < SI; ++r) {
     const u32 d = (u32)((key[r] >> shift) & mask);
     pos[r] += s_bin_start[d] + s_cnt[warp][d];
     s_keys[pos[r]] = key[r];
+    s_vals[pos[r]] = val[r];
   }
-  // ---- decoupled look-back (thread t <-> digit t): sum of the digit's counts over all earlier tiles.
-  //      LB_WINDOW predecessors are polled at once (independent loads in flight) and consumed in order, so a chain
-  //      of k aggregate-only predecessors costs ~k/LB_WINDOW memory round trips instead of k.
-  u32 excl_prev = 0;
-  {
+  if (tile != 0) {
     int p = tile - 1;
-    bool found = (tile == 0);
+    bool found = false;
     while (!found) {
       u32 sv[LB_WINDOW];
 #pragma unroll
       for (int i = 0; i < LB_WINDOW; ++i) {
-        sv[i] = LB_PREFIX;  // before the first tile: an empty inclusive prefix
+        sv[i] = LB_PREFIX;
         if (p - i >= 0) {
           const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
           asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv[i]) : "l"(ps) : "memory");
@@ -170,7 +173,7 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
 #pragma unroll
       for (int i = 0; i < LB_WINDOW; ++i) {
         if (found) break;
-        while ((sv[i] & LB_FLAGS) == 0u) {  // not published yet: poll this one
+        while ((sv[i] & LB_FLAGS) == 0u) {
           const u32* ps = const_cast<const u32*>(status) + (size_t)(p - i) * RADIX + t;
           asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(sv[i]) : "l"(ps) : "memory");
         }
@@ -179,29 +182,17 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
       }
       p -= LB_WINDOW;
     }
+    *my_status = LB_PREFIX | (excl_prev + bcount);
   }
-  if (tile != 0) *my_status = LB_PREFIX | (excl_prev + bcount);
-  s_gbase[t] = (int)((gh_incl - gh) + excl_prev) - (int)(bin_incl - bcount);
+  s_gbase[t] = (int)excl_prev - (int)(bin_incl - bcount);
   __syncthreads();
-  // ---- coalesced writes
-  int out[SI];
 #pragma unroll
   for (int i = 0; i < SI; ++i) {
     const int p = i * ST + t;
     const K k = s_keys[p];
-    const u32 d = (u32)((k >> shift) & mask);
-    out[i] = s_gbase[d] + p;
-    if (p < n_valid) kout[out[i]] = k;
-  }
-  __syncthreads();
-  u32* s_vals = reinterpret_cast<u32*>(s_keys);
-#pragma unroll
-  for (int r = 0; r < SI; ++r) s_vals[pos[r]] = val[r];
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < SI; ++i) {
-    const int p = i * ST + t;
-    if (p < n_valid) vout[out[i]] = s_vals[p];
+    const u32 v = s_vals[p];
+    const int o = s_gbase[(u32)((k >> shift) & mask)] + p;
+    if (p < n_valid) { kout[o] = k; vout[o] = v; }
   }
 }
 
@@ -209,13 +200,10 @@ radix_scatter_kernel(const K* __restrict__ kin, const u32* __restrict__ vin, K* 
 
 static long long sort_blocks(long long M, int items) { return (M + ST * items - 1) / (ST * items); }
 
-extern "C" void rs_sort_set_items(int items) { g_sort_items = (items == 16) ? 16 : 8; }
-extern "C" void rs_sort_set_window(int w) { g_sort_window = (w == 16) ? 16 : (w == 8 ? 8 : 4); }
-
 extern "C" long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit) {
   int npass = end_bit > begin_bit ? (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS : 0;
   if (npass > MAX_PASSES) npass = MAX_PASSES;
-  long long nb = sort_blocks(M > 0 ? M : 1, 8);  // sized for the smaller tile, enough for either setting
+  long long nb = sort_blocks(M > 0 ? M : 1, SITEMS);
   return (long long)MAX_PASSES * RADIX * 4 + 256 + (long long)npass * nb * RADIX * 4;
 }
 
@@ -244,25 +232,20 @@ static int sort_pairs_impl(K* ka, u32* va, K* kb, u32* vb, bool iota_vals, long 
       sh += nb;
     }
   }
-  const int items = g_sort_items;
-  const long long nblocks = sort_blocks(M, items);
+  const long long nblocks = sort_blocks(M, SITEMS);
   cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)rs_sort_pairs_temp_bytes(M, begin_bit, end_bit), st);
   if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
   u32* ghist = (u32*)temp;
   u32* tickets = (u32*)((char*)temp + MAX_PASSES * RADIX * 4);
   u32* status = (u32*)((char*)temp + MAX_PASSES * RADIX * 4 + 256);
   int hist_blocks = (int)(nblocks < 148 * 8 ? nblocks : 148 * 8);
-  const long long status_stride = sort_blocks(M, 8) * RADIX;
+  const long long status_stride = nblocks * RADIX;
   radix_hist_kernel<K><<<hist_blocks, ST, 0, st>>>(ka, M, n_dev, pi, ghist);
   for (int p = 0; p < npass; ++p) {
     const u32* vin = (p == 0 && iota_vals) ? nullptr : va;
-#define RS_LAUNCH_SCATTER(SI, LBW)                                                                              \
-  radix_scatter_kernel<K, SI, LBW><<<(unsigned)nblocks, ST, 0, st>>>(ka, vin, kb, vb, (int)M, n_dev, pi.shift[p], \
-                                                                     pi.mask[p], ghist + p * RADIX,             \
-                                                                     status + (size_t)p * status_stride, tickets + p)
-    if (items == 16) { if (g_sort_window == 16) RS_LAUNCH_SCATTER(16, 16); else if (g_sort_window == 8) RS_LAUNCH_SCATTER(16, 8); else RS_LAUNCH_SCATTER(16, 4); }
-    else { if (g_sort_window == 16) RS_LAUNCH_SCATTER(8, 16); else if (g_sort_window == 8) RS_LAUNCH_SCATTER(8, 8); else RS_LAUNCH_SCATTER(8, 4); }
-#undef RS_LAUNCH_SCATTER
+    radix_scatter_kernel<K, SITEMS, LBW><<<(unsigned)nblocks, ST, 0, st>>>(
+        ka, vin, kb, vb, (int)M, n_dev, pi.shift[p], pi.mask[p], ghist + p * RADIX,
+        status + (size_t)p * status_stride, tickets + p);
     K* tk = ka; ka = kb; kb = tk;
     u32* tv = va; va = vb; vb = tv;
   }

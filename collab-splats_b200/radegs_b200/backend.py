@@ -47,8 +47,6 @@ _SIGNATURES = {
     "rs_sort_pairs_u32": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_isect_finish32": (_i, [_p, _p, _p, _ll, _i, _i, _i, _p, _p, _p]),
     "rs_sort_pairs_temp_bytes": (_ll, [_ll, _i, _i]),
-    "rs_sort_set_items": (None, [_i]),
-    "rs_sort_set_window": (None, [_i]),
     "rs_sort_pairs": (_i, [_p, _p, _p, _p, _ll, _i, _i, _p, _ll, _p]),
     "rs_raster_padded_channels": (_i, [_i]),
     "rs_pack_geom": (_i, [_p, _p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p]),

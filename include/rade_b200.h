@@ -102,8 +102,6 @@ int rs_isect_emit_ordered(const float* means2d, const int32_t* radii, const floa
  * Stable, ascending, on key bits [begin_bit,end_bit).  Clobbers both buffer pairs.
  * Returns 0: result in (keys_b, vals_b); 1: result in (keys_a, vals_a); <0: error. */
 long long rs_sort_pairs_temp_bytes(long long M, int begin_bit, int end_bit);
-void rs_sort_set_items(int items_per_thread); /* tuning knob: 8 (default) or 16 keys per thread */
-void rs_sort_set_window(int predecessors);    /* tuning knob: look-back polling window 4 (default), 8 or 16 */
 int rs_sort_pairs(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long M,
                   int begin_bit, int end_bit, void* temp, long long temp_bytes, void* stream);
 /* Stable argsort of 32-bit keys: same contract and temp size (rs_sort_pairs_temp_bytes), but the value of pair i
