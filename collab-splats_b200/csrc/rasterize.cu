@@ -1136,12 +1136,17 @@ __global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const
         const float tt = q2.x + q2.y * dx + q2.z * dy;
         float w = v_dsum * tt + v_n0 * q3.x + v_n1 * q3.y + v_n2 * q3.z;
         {
+          // <v_c, colour>: four independent partial sums -- one accumulator would be a chain of DP dependent FMAs
+          // (4 cycles each), which the 2-4 resident warps per scheduler of the wide variants cannot hide
           const float4* cp = reinterpret_cast<const float4*>(&s.col[buf][jj][0]);
+          float w1 = 0.f, w2 = 0.f, w3 = 0.f;
 #pragma unroll
           for (int k = 0; k < DP / 4; ++k) {
             const float4 cc = cp[k];
-            w += v_c[4 * k] * cc.x + v_c[4 * k + 1] * cc.y + v_c[4 * k + 2] * cc.z + v_c[4 * k + 3] * cc.w;
+            w = fmaf(v_c[4 * k], cc.x, w); w1 = fmaf(v_c[4 * k + 1], cc.y, w1);
+            w2 = fmaf(v_c[4 * k + 2], cc.z, w2); w3 = fmaf(v_c[4 * k + 3], cc.w, w3);
           }
+          w = (w + w1) + (w2 + w3);
         }
         const float v_alpha = T * w - R * ra + tfin_term * ra;
         R += vis * w;
