@@ -43,6 +43,30 @@ template <> struct X<float> {
 };
 #endif
 
+// Reciprocal / square root of the "ordinary arithmetic" sections (RaDe terms, the whole backward): exact on the host and
+// in double, the SFU approximations (1-2 ulp) for float on the device.  An IEEE fp32 division is ~12 instructions with a
+// slow-path call; the projection VJP had 38 of them per element.
+template <typename T> RS_HD T rcp_(T x) { return T(1) / x; }
+template <typename T> RS_HD T sqrt_fast(T x) { return sqrt(x); }
+template <typename T> RS_HD T rsqrt_fast(T x) { return T(1) / sqrt(x); }
+#if defined(__CUDA_ARCH__)
+template <> __device__ __forceinline__ float rcp_<float>(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <> __device__ __forceinline__ float sqrt_fast<float>(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <> __device__ __forceinline__ float rsqrt_fast<float>(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#endif
+
 template <typename T> struct Cam {
   T W[9];  // rotation, row-major (world -> camera)
   T t[3];
@@ -74,6 +98,7 @@ template <typename T> struct ProjCtx {
   T det0, c00b, c11b, detraw, det, ratio;
   // RaDe
   T aw[3], bl[3], cw[3], n[3], nn, h[3], d, vbn, w[3], pl0, pl1, l2, l, fac, g0, g1, cn[3], cnn;
+  T is2[3], inn, ivbn, il, il2, icnn;   // reciprocals of scale^2, nn, vbn, l, l2, cnn (shared with the backward)
   bool rade_ok, valid;
 };
 
@@ -194,41 +219,49 @@ RS_HD void project_core(const T* mean, const T* quat, const T* scale, const Cam<
 #pragma unroll
   for (int j = 0; j < 3; ++j) k.aw[j] = Wm[j] * u + Wm[3 + j] * v + Wm[6 + j];
 #pragma unroll
-  for (int q = 0; q < 3; ++q)
-    k.bl[q] = (Rm[q] * k.aw[0] + Rm[3 + q] * k.aw[1] + Rm[6 + q] * k.aw[2]) / (scale[q] * scale[q]);
+  for (int q = 0; q < 3; ++q) {
+    k.is2[q] = rcp_(scale[q] * scale[q]);
+    k.bl[q] = (Rm[q] * k.aw[0] + Rm[3 + q] * k.aw[1] + Rm[6 + q] * k.aw[2]) * k.is2[q];
+  }
 #pragma unroll
   for (int j = 0; j < 3; ++j) k.cw[j] = Rm[j * 3] * k.bl[0] + Rm[j * 3 + 1] * k.bl[1] + Rm[j * 3 + 2] * k.bl[2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) k.n[i] = Wm[i * 3] * k.cw[0] + Wm[i * 3 + 1] * k.cw[1] + Wm[i * 3 + 2] * k.cw[2];
-  k.nn = sqrt(k.n[0] * k.n[0] + k.n[1] * k.n[1] + k.n[2] * k.n[2]);
+  k.nn = sqrt_fast(k.n[0] * k.n[0] + k.n[1] * k.n[1] + k.n[2] * k.n[2]);
   bool ok = isfinite(k.nn) && (k.nn > T(0));
   T nns = ok ? k.nn : T(1);
+  k.inn = rcp_(nns);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) k.h[i] = k.n[i] / nns;
+  for (int i = 0; i < 3; ++i) k.h[i] = k.n[i] * k.inn;
   k.d = k.h[0] * u + k.h[1] * v + k.h[2];
   k.vbn = fmax(k.d, T(RS_VBN_EPS));
+  k.ivbn = rcp_(k.vbn);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) k.w[i] = k.h[i] / k.vbn;
+  for (int i = 0; i < 3; ++i) k.w[i] = k.h[i] * k.ivbn;
   T uv = u * v;
   k.pl0 = (v * v + T(1)) * k.w[0] - uv * k.w[1] - u * k.w[2];
   k.pl1 = -uv * k.w[0] + (u * u + T(1)) * k.w[1] - v * k.w[2];
   k.l2 = u * u + v * v + T(1);
-  k.l = sqrt(k.tx * k.tx + k.ty * k.ty + k.z * k.z);
-  k.fac = k.l / k.l2;
+  k.l = sqrt_fast(k.tx * k.tx + k.ty * k.ty + k.z * k.z);
+  k.il = rcp_(k.l);
+  k.il2 = rcp_(k.l2);
+  k.fac = k.l * k.il2;
   k.g0 = k.pl0 * k.fac;
   k.g1 = k.pl1 * k.fac;
-  k.cn[0] = -k.g0 * rz - k.tx / k.l;
-  k.cn[1] = -k.g1 * rz - k.ty / k.l;
-  k.cn[2] = (k.g0 * k.tx + k.g1 * k.ty) * k.rz2 - k.z / k.l;
-  k.cnn = sqrt(k.cn[0] * k.cn[0] + k.cn[1] * k.cn[1] + k.cn[2] * k.cn[2]);
+  k.cn[0] = -k.g0 * rz - k.tx * k.il;
+  k.cn[1] = -k.g1 * rz - k.ty * k.il;
+  k.cn[2] = (k.g0 * k.tx + k.g1 * k.ty) * k.rz2 - k.z * k.il;
+  k.cnn = sqrt_fast(k.cn[0] * k.cn[0] + k.cn[1] * k.cn[1] + k.cn[2] * k.cn[2]);
   ok = ok && isfinite(k.cnn) && (k.cnn > T(0));
   k.rade_ok = ok;
   if (ok) {
+    k.icnn = rcp_(k.cnn);
     o.ray_t = k.l;
-    o.rp0 = k.g0 / fx;
-    o.rp1 = k.g1 / fy;
-    o.nx = k.cn[0] / k.cnn; o.ny = k.cn[1] / k.cnn; o.nz = k.cn[2] / k.cnn;
+    o.rp0 = k.g0 * rcp_(fx);
+    o.rp1 = k.g1 * rcp_(fy);
+    o.nx = k.cn[0] * k.icnn; o.ny = k.cn[1] * k.icnn; o.nz = k.cn[2] * k.icnn;
   } else {
+    k.icnn = T(0);
     o.ray_t = o.rp0 = o.rp1 = o.nx = o.ny = o.nz = T(0);
   }
   if (!valid) {
@@ -270,21 +303,21 @@ RS_HD void project_bwd_one(const T* mean, const T* quat, const T* scale, const C
 
   // ---------------- RaDe stage
   if (k.rade_ok) {
-    T N0 = k.cn[0] / k.cnn, N1 = k.cn[1] / k.cnn, N2 = k.cn[2] / k.cnn;
+    T N0 = k.cn[0] * k.icnn, N1 = k.cn[1] * k.icnn, N2 = k.cn[2] * k.icnn;
     T nd = N0 * g.v_nx + N1 * g.v_ny + N2 * g.v_nz;
-    T vcn0 = (g.v_nx - N0 * nd) / k.cnn, vcn1 = (g.v_ny - N1 * nd) / k.cnn, vcn2 = (g.v_nz - N2 * nd) / k.cnn;
-    T il = T(1) / k.l;
-    T v_g0 = g.v_rp0 / fx - vcn0 * rz + vcn2 * k.tx * rz2;
-    T v_g1 = g.v_rp1 / fy - vcn1 * rz + vcn2 * k.ty * rz2;
+    T vcn0 = (g.v_nx - N0 * nd) * k.icnn, vcn1 = (g.v_ny - N1 * nd) * k.icnn, vcn2 = (g.v_nz - N2 * nd) * k.icnn;
+    T il = k.il;
+    T v_g0 = g.v_rp0 * rcp_(fx) - vcn0 * rz + vcn2 * k.tx * rz2;
+    T v_g1 = g.v_rp1 * rcp_(fy) - vcn1 * rz + vcn2 * k.ty * rz2;
     v_rz += -k.g0 * vcn0 - k.g1 * vcn1;
     v_rz2 += (k.g0 * k.tx + k.g1 * k.ty) * vcn2;
     v_tx += -vcn0 * il + k.g0 * rz2 * vcn2;
     v_ty += -vcn1 * il + k.g1 * rz2 * vcn2;
     v_z += -vcn2 * il;
     T v_fac = k.pl0 * v_g0 + k.pl1 * v_g1;
-    T v_l = (k.tx * vcn0 + k.ty * vcn1 + k.z * vcn2) * il * il + g.v_ray_t + v_fac / k.l2;
+    T v_l = (k.tx * vcn0 + k.ty * vcn1 + k.z * vcn2) * il * il + g.v_ray_t + v_fac * k.il2;
     T v_pl0 = k.fac * v_g0, v_pl1 = k.fac * v_g1;
-    T v_l2 = -k.fac / k.l2 * v_fac;
+    T v_l2 = -k.fac * k.il2 * v_fac;
     v_tx += k.tx * il * v_l;
     v_ty += k.ty * il * v_l;
     v_z += k.z * il * v_l;
@@ -296,7 +329,7 @@ RS_HD void project_bwd_one(const T* mean, const T* quat, const T* scale, const C
     T vw2 = -u * v_pl0 - v * v_pl1;
     v_u += (-v * k.w[1] - k.w[2]) * v_pl0 + (-v * k.w[0] + T(2) * u * k.w[1]) * v_pl1;
     v_v += (T(2) * v * k.w[0] - u * k.w[1]) * v_pl0 + (-u * k.w[0] - k.w[2]) * v_pl1;
-    T ivbn = T(1) / k.vbn;
+    T ivbn = k.ivbn;
     T vh0 = vw0 * ivbn, vh1 = vw1 * ivbn, vh2 = vw2 * ivbn;
     T v_vbn = -(k.w[0] * vw0 + k.w[1] * vw1 + k.w[2] * vw2) * ivbn;
     T v_d = (k.d >= T(RS_VBN_EPS)) ? v_vbn : T(0);
@@ -304,7 +337,7 @@ RS_HD void project_bwd_one(const T* mean, const T* quat, const T* scale, const C
     v_u += v_d * k.h[0];
     v_v += v_d * k.h[1];
     T hd = k.h[0] * vh0 + k.h[1] * vh1 + k.h[2] * vh2;
-    T vn[3] = {(vh0 - k.h[0] * hd) / k.nn, (vh1 - k.h[1] * hd) / k.nn, (vh2 - k.h[2] * hd) / k.nn};
+    T vn[3] = {(vh0 - k.h[0] * hd) * k.inn, (vh1 - k.h[1] * hd) * k.inn, (vh2 - k.h[2] * hd) * k.inn};
     T vcw[3], vbl[3], ve[3], vaw[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) vcw[j] = Wm[j] * vn[0] + Wm[3 + j] * vn[1] + Wm[6 + j] * vn[2];
@@ -316,8 +349,8 @@ RS_HD void project_bwd_one(const T* mean, const T* quat, const T* scale, const C
       for (int q = 0; q < 3; ++q) vR[j * 3 + q] += vcw[j] * k.bl[q];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      ve[q] = vbl[q] / (scale[q] * scale[q]);
-      vs[q] += -T(2) * k.bl[q] / scale[q] * vbl[q];
+      ve[q] = vbl[q] * k.is2[q];
+      vs[q] += -T(2) * k.bl[q] * (scale[q] * k.is2[q]) * vbl[q];
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -343,14 +376,13 @@ RS_HD void project_bwd_one(const T* mean, const T* quat, const T* scale, const C
   }
 
   // ---------------- blur / conic stage
-  T idet = T(1) / k.det;
+  T idet = rcp_(k.det);
   T v_c11b = g.v_ca * idet, v_c01 = -g.v_cb * idet, v_c00b = g.v_cc * idet;
   T ca = k.c11b * idet, cb = -k.c01 * idet, cc = k.c00b * idet;
   T v_det = -(g.v_ca * ca + g.v_cb * cb + g.v_cc * cc) * idet;
   T v_det0 = 0;
   if (k.ratio > T(0) && g.v_comp != T(0)) {
-    T comp = sqrt(k.ratio);
-    T v_ratio = g.v_comp * T(0.5) / comp;
+    T v_ratio = g.v_comp * T(0.5) * rsqrt_fast(k.ratio);
     v_det0 = v_ratio * idet;
     v_det += -k.ratio * idet * v_ratio;
   }
