@@ -135,11 +135,18 @@ class ShGradExchange:
         self.mode = mode
         if push_engine not in ("dma", "sm"):
             raise ValueError("push_engine must be 'dma' (copy engines) or 'sm' (store kernel)")
-        # CTAs per peer of the SM store kernel; 0 = by payload: 4 up to 24 MB per peer, 8 above (8 GPUs, NVSwitch: at
-        # 16 MB per peer the copy engines deliver 384 GB/s and hold the step at 2.74 ms, 4 CTAs per peer 2.60 ms; at
-        # 48 MB per peer 8 CTAs win, profiles/r02_exchange_ab_n8.txt)
+        # CTAs per peer of the SM store kernel; 0 = automatic.  The pushes overlap the projection VJP, so their CTAs
+        # take SMs from it, while the bandwidth they need is bounded by the number of peers: about 32 pushing CTAs in
+        # total is the measured optimum -- 8 GPUs at 16 MB per peer: 4 per peer 2.60 ms/step, 8: 2.68, 16: 2.70, copy
+        # engines 2.74; 2 GPUs (one peer, which 4 CTAs cannot saturate): 4: 2.42 ms, 8-32: 2.39; at 48 MB per peer
+        # (config 4) 8 per peer win at 8 GPUs (profiles/r02_exchange_ab_n8.txt, r02_push_ctas_n2.txt)
         self.push_engine = push_engine
-        self.push_ctas = int(push_ctas) if int(push_ctas) > 0 else (4 if self.region_bytes <= 24 * 2 ** 20 else 8)
+        if int(push_ctas) > 0:
+            self.push_ctas = int(push_ctas)
+        else:
+            peers = max(self.world - 1, 1)
+            floor = 4 if self.region_bytes <= 24 * 2 ** 20 else 8
+            self.push_ctas = max(floor, min(16, 32 // peers))
         self._peer_ptrs = []        # imported mappings, closed in close()
         self._own = []              # own cudaMalloc'ed blocks
         cams = [self.C] * self.world
