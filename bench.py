@@ -310,9 +310,17 @@ class Workload:
         with ex:
             loss.backward()
 
+    def _mark(self, name):
+        log = getattr(self, "phase_log", None)
+        if log is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            log.append((name, ev))
+
     def allreduce_grads(self):
         import torch.distributed as dist
         ex = getattr(self, "exchange", None)
+        self._mark("backward_done")
         small = [v.grad.reshape(-1) for k, v in self.params.items() if k != "sh_coeffs"]
         work = None
         if self.peer_ar is not None:
@@ -333,10 +341,12 @@ class Workload:
             for w in self.pending:
                 w.wait()
             self.pending.clear()
+        self._mark("sh_gradient_done")
         if work is not None:
             work.wait()
         else:
             torch.cuda.current_stream(self.device).wait_stream(self.ar_stream)
+        self._mark("small_allreduce_done")
         return flat
 
 
@@ -681,7 +691,21 @@ def multi_gpu_diagnostics(wl, world, device, lib, backend, resident, push_engine
     lib.rs_timing_enable(0)
     keys = ("rs_sh_colors_bwd_local", "rs_peer_signal", "rs_peer_wait", "rs_sh_coeffs_gather", "rs_sh_colors_bwd",
             "rs_peer_allreduce")
+    # where the step's tail goes on this rank's main stream: events at the end of the backward, after the SH gradient
+    # (flag wait + gather kernel) and after the all-reduce of the other gradients has been joined
+    wl.phase_log = []
+    n_ph = 10
+    for _ in range(n_ph):
+        wl._mark("step_start")
+        resident()
+    wl._mark("step_start")
+    torch.cuda.synchronize(device)
+    log, wl.phase_log = wl.phase_log, None
+    tail = {}
+    for (na, ea), (nb_, eb) in zip(log[:-1], log[1:]):
+        tail[f"{na}->{nb_}"] = tail.get(f"{na}->{nb_}", 0.0) + ea.elapsed_time(eb) / n_ph
     return {"compute_only_ms_per_rank": [round(float(v[0]), 4) for v in everyone],
+            "main_stream_phases_ms_rank0": {k: round(v, 4) for k, v in tail.items()},
             "n_isects_per_rank": [int(v[1]) for v in everyone],
             "exchange_spans_ms_rank0": {k: round(spans[k][0] / 5, 4) for k in keys if k in spans},
             "grad_exchange": wl.exchange_mode + ("/" + push_engine if wl.exchange_mode == "push" else ""),
@@ -709,6 +733,7 @@ def run_config4(args, device, rank, world, lib, backend):
         flat = resident()
     identical = None
     if world > 1:
+        flat = resident()
         identical = assert_replicas_identical(wl, flat, world, device)
     steps = max(3, min(args.steps, 10))
     l0 = lib.rs_launch_count()
