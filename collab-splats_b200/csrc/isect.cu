@@ -16,9 +16,10 @@ constexpr int IB = 256;
 __device__ __forceinline__ bool tile_bbox(float2 m, int2 r, int tile_w, int tile_h, int& xmin, int& ymin, int& xmax,
                                           int& ymax) {
   if (r.x <= 0 || r.y <= 0) return false;
-  const float ts = (float)RS_TILE;
-  float tx = __fdiv_rn(m.x, ts), ty = __fdiv_rn(m.y, ts);
-  float rx = __fdiv_rn((float)r.x, ts), ry = __fdiv_rn((float)r.y, ts);
+  static_assert((RS_TILE & (RS_TILE - 1)) == 0, "tile size is a power of two: x / tile == x * (1 / tile) bit for bit");
+  const float its = 1.0f / (float)RS_TILE;
+  float tx = __fmul_rn(m.x, its), ty = __fmul_rn(m.y, its);
+  float rx = __fmul_rn((float)r.x, its), ry = __fmul_rn((float)r.y, its);
   float fx0 = floorf(__fsub_rn(tx, rx)), fy0 = floorf(__fsub_rn(ty, ry));
   float fx1 = ceilf(__fadd_rn(tx, rx)), fy1 = ceilf(__fadd_rn(ty, ry));
   xmin = (int)fminf(fmaxf(fx0, 0.f), (float)tile_w);
@@ -310,27 +311,45 @@ isect_finish32_kernel(const unsigned int* __restrict__ keys32, const int32_t* __
 __global__ void __launch_bounds__(IB)
 offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, const long long* __restrict__ n_dev,
                      int n_tiles, int tile_bits, int total, int32_t* __restrict__ offsets) {
-  const long long i = (long long)blockIdx.x * IB + threadIdx.x;
+  // four consecutive keys per thread (two 16-byte loads in flight) + the key before them: the kernel only reads, so
+  // its speed is the number of bytes each thread keeps in flight
+  constexpr int KPT = 4;
+  const long long th = (long long)blockIdx.x * IB + threadIdx.x;
   if (n_dev) {   // device-side count: M is the capacity the grid was sized for
     M = min(M, __ldg(n_dev));
     if (M == 0) {
-      if (i < total) offsets[i] = 0;   // (the grid covers at least `total` threads in this mode)
+      if (th < total) offsets[th] = 0;   // (the grid covers at least `total` threads in this mode)
       return;
     }
   }
-  if (i >= M) return;
+  const long long i0 = th * KPT;
+  if (i0 >= M) return;
   const unsigned long long tmask = (1ull << tile_bits) - 1ull;
-  unsigned long long k = (unsigned long long)__ldg(isect_ids + i) >> 32;
-  long long cur = (long long)(k >> tile_bits) * n_tiles + (long long)(k & tmask);
-  if (i == 0) {
-    for (long long t = 0; t <= cur; ++t) offsets[t] = 0;
+  unsigned long long key[KPT];
+  if (i0 + KPT <= M && (reinterpret_cast<uintptr_t>(isect_ids) & 15) == 0) {
+    const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(isect_ids + i0));
+    const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(isect_ids + i0) + 1);
+    key[0] = a.x; key[1] = a.y; key[2] = b.x; key[3] = b.y;
   } else {
-    unsigned long long kp = (unsigned long long)__ldg(isect_ids + i - 1) >> 32;
-    long long prev = (long long)(kp >> tile_bits) * n_tiles + (long long)(kp & tmask);
-    for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) key[j] = i0 + j < M ? (unsigned long long)__ldg(isect_ids + i0 + j) : 0ull;
   }
-  if (i == M - 1) {
-    for (long long t = cur + 1; t < total; ++t) offsets[t] = (int32_t)M;
+  long long prev = -1;   // linear tile index of the entry before: "-1" makes entry 0 fill offsets[0..cur] with 0
+  if (i0 > 0) {
+    const unsigned long long kp = (unsigned long long)__ldg(isect_ids + i0 - 1) >> 32;
+    prev = (long long)(kp >> tile_bits) * n_tiles + (long long)(kp & tmask);
+  }
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const long long i = i0 + j;
+    if (i >= M) break;
+    const unsigned long long k = key[j] >> 32;
+    const long long cur = (long long)(k >> tile_bits) * n_tiles + (long long)(k & tmask);
+    for (long long t = prev + 1; t <= cur; ++t) offsets[t] = (int32_t)i;
+    prev = cur;
+    if (i == M - 1) {
+      for (long long t = cur + 1; t < total; ++t) offsets[t] = (int32_t)M;
+    }
   }
 }
 
@@ -457,7 +476,7 @@ extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, 
     return RS_OK;
   }
   if (!isect_ids) return RS_ERR_BAD_ARG;
-  offset_encode_kernel<<<rs_div_up(M, IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, nullptr, (int)n_tiles,
+  offset_encode_kernel<<<rs_div_up(rs_div_up(M, 4), IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, nullptr, (int)n_tiles,
                                                                         tile_bits_for(n_tiles), (int)total, offsets);
   RS_RETURN_LAST_ERROR();
 }
@@ -470,7 +489,7 @@ extern "C" int rs_offset_encode_dev(const long long* isect_ids, long long capaci
     return RS_ERR_BAD_ARG;
   if (capacity >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   const long long n_tiles = (long long)tile_w * tile_h, total = n_tiles * C;
-  const long long threads = capacity > total ? capacity : total;
+  const long long threads = (capacity + 3) / 4 > total ? (capacity + 3) / 4 : total;
   offset_encode_kernel<<<rs_div_up(threads, IB), IB, 0, (cudaStream_t)stream>>>(
       isect_ids, capacity, n_isects_dev, (int)n_tiles, tile_bits_for(n_tiles), (int)total, offsets);
   RS_RETURN_LAST_ERROR();

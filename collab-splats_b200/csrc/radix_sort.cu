@@ -42,7 +42,19 @@ radix_hist_kernel(const K* __restrict__ keys, long long M, const long long* __re
   for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += ST) sh[i] = 0;
   __syncthreads();
   const long long stride = (long long)gridDim.x * ST;
-  for (long long i = (long long)blockIdx.x * ST + threadIdx.x; i < M; i += stride) {
+  constexpr int UN = 4;   // keys in flight per thread: the pass only reads, its speed is its memory-level parallelism
+  long long i = (long long)blockIdx.x * ST + threadIdx.x;
+  for (; i + (UN - 1) * stride < M; i += UN * stride) {
+    K k[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) k[u] = __ldg(keys + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int p = 0; p < MAX_PASSES; ++p)
+        if (p < pi.n) atomicAdd(&sh[p * RADIX + (u32)((k[u] >> pi.shift[p]) & pi.mask[p])], 1u);
+  }
+  for (; i < M; i += stride) {
     K k = __ldg(keys + i);
 #pragma unroll
     for (int p = 0; p < MAX_PASSES; ++p)
