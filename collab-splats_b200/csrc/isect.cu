@@ -310,13 +310,15 @@ isect_finish32_kernel(const unsigned int* __restrict__ keys32, const int32_t* __
 
 __global__ void __launch_bounds__(IB)
 offset_encode_kernel(const long long* __restrict__ isect_ids, long long M, const long long* __restrict__ n_dev,
-                     int n_tiles, int tile_bits, int total, int32_t* __restrict__ offsets) {
+                     int n_tiles, int tile_bits, int total, int32_t* __restrict__ offsets,
+                     int32_t* __restrict__ n_clamped) {
   // four consecutive keys per thread (two 16-byte loads in flight) + the key before them: the kernel only reads, so
   // its speed is the number of bytes each thread keeps in flight
   constexpr int KPT = 4;
   const long long th = (long long)blockIdx.x * IB + threadIdx.x;
   if (n_dev) {   // device-side count: M is the capacity the grid was sized for
     M = min(M, __ldg(n_dev));
+    if (th == 0 && n_clamped) *n_clamped = (int32_t)M;   // what the compositing kernels read as the end of the last list
     if (M == 0) {
       if (th < total) offsets[th] = 0;   // (the grid covers at least `total` threads in this mode)
       return;
@@ -477,21 +479,21 @@ extern "C" int rs_offset_encode(const long long* isect_ids, long long M, int C, 
   }
   if (!isect_ids) return RS_ERR_BAD_ARG;
   offset_encode_kernel<<<rs_div_up(rs_div_up(M, 4), IB), IB, 0, (cudaStream_t)stream>>>(isect_ids, M, nullptr, (int)n_tiles,
-                                                                        tile_bits_for(n_tiles), (int)total, offsets);
+                                                                        tile_bits_for(n_tiles), (int)total, offsets, nullptr);
   RS_RETURN_LAST_ERROR();
 }
 
 // Sync-free form: the number of sorted keys is min(*n_isects_dev, capacity), read on the device.
 extern "C" int rs_offset_encode_dev(const long long* isect_ids, long long capacity, const long long* n_isects_dev, int C,
-                                    int tile_w, int tile_h, int32_t* offsets, void* stream) {
+                                    int tile_w, int tile_h, int32_t* offsets, int32_t* n_valid, void* stream) {
   RsSpan span__("rs_offset_encode", stream);
-  if (capacity <= 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets || !isect_ids || !n_isects_dev)
+  if (capacity <= 0 || C <= 0 || tile_w <= 0 || tile_h <= 0 || !offsets || !isect_ids || !n_isects_dev || !n_valid)
     return RS_ERR_BAD_ARG;
   if (capacity >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   const long long n_tiles = (long long)tile_w * tile_h, total = n_tiles * C;
   const long long threads = (capacity + 3) / 4 > total ? (capacity + 3) / 4 : total;
   offset_encode_kernel<<<rs_div_up(threads, IB), IB, 0, (cudaStream_t)stream>>>(
-      isect_ids, capacity, n_isects_dev, (int)n_tiles, tile_bits_for(n_tiles), (int)total, offsets);
+      isect_ids, capacity, n_isects_dev, (int)n_tiles, tile_bits_for(n_tiles), (int)total, offsets, n_valid);
   RS_RETURN_LAST_ERROR();
 }
 

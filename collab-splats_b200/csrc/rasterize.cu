@@ -174,7 +174,6 @@ struct RasterArgs {
   const int* offsets;        // [C*tile_h*tile_w]
   const int* flatten_ids;    // [M]
   int M;
-  const long long* M_dev;    // device-side count (sync-free callers; M is then the buffers' capacity), or null
   // forward outputs == backward saved tensors
   float* out_colors;   // [C,H,W,D]
   float* out_alphas;   // [C,H,W]
@@ -191,6 +190,8 @@ struct RasterArgs {
   float* abs_grad;     // [C*N][2] or null
   unsigned long long* stats;  // forward, optional: {Q pairs a per-pixel loop would visit, Qc contributing pairs,
                               //                     warp evaluations, warp evaluations that blended}
+  const int* end_dev;  // sync-free callers: device int32 = number of valid list entries (<= M, which is then the
+                       // buffers' capacity), written by rs_offset_encode_dev; null: M is the count
 };
 
 template <int DP, int BATCH, int S = 2> struct Smem {
@@ -295,9 +296,20 @@ __device__ __forceinline__ void ring_gather_share(Smem<DP, BATCH, S>& s, int sta
   mbar_arrive_after_cp_async(&s.full[stage]);
 }
 
-// end of the last tile's list: the number of intersections, read from the device when the caller never learned it
-__device__ __forceinline__ int list_end(const RasterArgs& a) {
-  return a.M_dev ? (int)min((long long)a.M, __ldg(a.M_dev)) : a.M;
+// End of a tile's list: the next tile's offset, or for the last tile the number of intersections -- a kernel parameter
+// (DEV = false) or, when the caller never learned it (sync-free), a device word (DEV = true: one load through a selected
+// pointer, no branch).  The 2-pixel kernels are compiled for both (a run-time test here costs the forward 8 registers
+// and a CTA per SM); the generic kernels test at run time.
+template <bool DEV>
+__device__ __forceinline__ int list_end_of(const RasterArgs& a, int tile_id, int n_tiles) {
+  if constexpr (DEV) {
+    return __ldg(tile_id + 1 < n_tiles ? a.offsets + tile_id + 1 : a.end_dev);
+  } else {
+    return tile_id + 1 < n_tiles ? __ldg(a.offsets + tile_id + 1) : a.M;
+  }
+}
+__device__ __forceinline__ int list_end_rt(const RasterArgs& a, int tile_id, int n_tiles) {
+  return a.end_dev ? list_end_of<true>(a, tile_id, n_tiles) : list_end_of<false>(a, tile_id, n_tiles);
 }
 
 struct TileCtx {
@@ -314,7 +326,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const RasterArgs& a, int lane, int w
   const int tl = tile_id - c.cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   c.start = __ldg(a.offsets + tile_id);
-  c.end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
+  c.end = list_end_rt(a, tile_id, a.C * tiles_per_cam);
   c.x0 = txi * RS_TILE + (warp & 1) * 8;
   c.y0 = tyi * RS_TILE + (warp >> 1) * 4;
   c.pxi = c.x0 + (lane & 7);
@@ -699,8 +711,10 @@ __device__ __forceinline__ float sigma_col(float adx2, float bdx, float c, float
 // count of the (issue-bound) alpha test; 4 warps (128 threads) per tile, 128-Gaussian batches.
 constexpr int RT2 = 128;
 
-template <int DP, int BATCH, bool STATS, int NW, int S = 2>
-__global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArgs a) {
+template <int DP, int BATCH, bool STATS, int NW, int S = 2, bool EDEV = false>
+// (S == 2, the default barrier staging: capped at 72 registers = 7 CTAs of 128 threads per SM; the allocation drifts to
+// 80 registers / 6 CTAs otherwise, which costs the forward 5 %)
+__global__ void __launch_bounds__(NW * 32, (S == 2 && NW == 4) ? 0 : 6) rasterize_fwd2_kernel(const RasterArgs a) {
   constexpr int NT = NW * 32, SUB = 4 / NW;   // NW warps per CTA: a CTA covers NW of the tile's four 8x8 blocks
   static_assert(S == 2 || BATCH == NT, "ring: one slot per thread");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -713,7 +727,7 @@ __global__ void __launch_bounds__(NW * 32) rasterize_fwd2_kernel(const RasterArg
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
+  const int end = list_end_of<EDEV>(a, tile_id, a.C * tiles_per_cam);
   const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const int pyi[2] = {y0 + (lane >> 3), y0 + (lane >> 3) + 4};
@@ -1254,7 +1268,7 @@ __global__ void __launch_bounds__(RT, (CMMA ? 2 : 0)) rasterize_bwd_kernel(const
 // x-dependent terms and -- the point of the variant -- ONE 16-value warp reduction and ONE 64-byte RED per
 // (warp, Gaussian): their contributions are summed in registers first.  Because dx is common to the two pixels
 // the record's moments factor as dx * (sum over the two pixels), which removes most per-pixel multiplies.
-template <int BATCH, bool ABSGRAD, int MINB, int NW, int S = 2>
+template <int BATCH, bool ABSGRAD, int MINB, int NW, int S = 2, bool EDEV = false>
 __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kernel(const RasterArgs a) {
   constexpr int DP = 4;
   constexpr int NT = NW * 32, SUB = 4 / NW, IPT = BATCH / NT;   // NW warps per CTA; IPT ids per thread and batch
@@ -1270,7 +1284,7 @@ __global__ void __launch_bounds__(NW * 32, MINB * (4 / NW)) rasterize_bwd2_kerne
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
+  const int end = list_end_of<EDEV>(a, tile_id, a.C * tiles_per_cam);
   const int x0 = txi * RS_TILE + (qd & 1) * 8, y0 = tyi * RS_TILE + (qd >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const float px = pxi + 0.5f;
@@ -1665,7 +1679,7 @@ __device__ __forceinline__ void bwd3_flush(Bwd3Warp& w, const Bwd3Cta& wc, int n
   }
 }
 
-template <int BATCH, int MINB>
+template <int BATCH, int MINB, bool EDEV = false>
 __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterArgs a) {
   constexpr int DP = 4;
   static_assert(BATCH <= RT2, "at most one id per thread");
@@ -1680,7 +1694,7 @@ __global__ void __launch_bounds__(RT2, MINB) rasterize_bwd3_kernel(const RasterA
   const int tl = tile_id - cam * tiles_per_cam;
   const int tyi = tl / a.tile_w, txi = tl - tyi * a.tile_w;
   const int start = __ldg(a.offsets + tile_id);
-  const int end = (tile_id + 1 < a.C * tiles_per_cam) ? __ldg(a.offsets + tile_id + 1) : list_end(a);
+  const int end = list_end_of<EDEV>(a, tile_id, a.C * tiles_per_cam);
   const int x0 = txi * RS_TILE + (warp & 1) * 8, y0 = tyi * RS_TILE + (warp >> 1) * 8;
   const int pxi = x0 + (lane & 7);
   const float px = pxi + 0.5f;
@@ -1888,9 +1902,16 @@ template <int DP> int launch_fwd(const RasterArgs& a, cudaStream_t st) {
       const int tiles = a.C * a.tile_w * a.tile_h;
       // (CTAs of 2 or 1 warps -- half / quarter tiles, no or less barrier coupling -- were measured slower: every CTA
       // gathers the whole tile list, profiles/r02_warps_per_cta_ab.txt)
-      if (a.stats) rasterize_fwd2_kernel<DP, B2, true, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);  // counting only
-      else if (a.flags & F_FWD_RING) rasterize_fwd2_kernel<DP, B2, false, 4, 3><<<tiles, 128, sizeof(Smem<DP, B2, 3>), st>>>(a);
-      else rasterize_fwd2_kernel<DP, B2, false, 4><<<tiles, 128, sizeof(Smem<DP, B2>), st>>>(a);
+      // (every variant exists for a host-side and a device-side intersection count, see list_end_of)
+#define RS_FWD2(STATS_, S_)                                                                                          \
+  do {                                                                                                               \
+    if (a.end_dev) rasterize_fwd2_kernel<DP, B2, STATS_, 4, S_, true><<<tiles, 128, sizeof(Smem<DP, B2, S_>), st>>>(a); \
+    else rasterize_fwd2_kernel<DP, B2, STATS_, 4, S_, false><<<tiles, 128, sizeof(Smem<DP, B2, S_>), st>>>(a);       \
+  } while (0)
+      if (a.stats) RS_FWD2(true, 2);  // counting only
+      else if (a.flags & F_FWD_RING) RS_FWD2(false, 3);
+      else RS_FWD2(false, 2);
+#undef RS_FWD2
       RS_RETURN_LAST_ERROR();
     }
     if (a.stats) return launch_fwd2<DP, true>(a, st);  // instrumented variant (counting only, never timed)
@@ -1931,22 +1952,32 @@ template <int DP> int launch_bwd(const RasterArgs& a, cudaStream_t st) {
 #define RS_LAUNCH_BWD3(BT, MINB)                                                                                    \
   do {                                                                                                              \
     const size_t smem3 = sizeof(Smem<DP, BT>) + (RT2 / 32) * sizeof(Bwd3Warp) + sizeof(Bwd3Cta);                    \
-    cudaError_t e = cudaFuncSetAttribute(rasterize_bwd3_kernel<BT, MINB>,                                           \
+    cudaError_t e = cudaFuncSetAttribute(rasterize_bwd3_kernel<BT, MINB, false>,                                    \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);                  \
+    if (e == cudaSuccess)                                                                                           \
+      e = cudaFuncSetAttribute(rasterize_bwd3_kernel<BT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                               (int)smem3);                                                                         \
     if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }                                 \
-    rasterize_bwd3_kernel<BT, MINB><<<grid, RT2, smem3, st>>>(a);                                                   \
+    if (a.end_dev) rasterize_bwd3_kernel<BT, MINB, true><<<grid, RT2, smem3, st>>>(a);                              \
+    else rasterize_bwd3_kernel<BT, MINB, false><<<grid, RT2, smem3, st>>>(a);                                       \
   } while (0)
         if (tune == 1) RS_LAUNCH_BWD3(128, 3);
         else RS_LAUNCH_BWD3(64, 4);
 #undef RS_LAUNCH_BWD3
         RS_RETURN_LAST_ERROR();
       }
-      if (a.abs_grad) rasterize_bwd2_kernel<B2, true, 4, 4><<<grid, RT2, smem, st>>>(a);
-      else if (tune == 7) rasterize_bwd2_kernel<B2, false, 7, 4><<<grid, RT2, smem, st>>>(a);
-      else if (tune == 6) rasterize_bwd2_kernel<B2, false, 6, 4><<<grid, RT2, smem, st>>>(a);
-      else if (a.flags & F_BWD_BARRIER) rasterize_bwd2_kernel<B2, false, 4, 4><<<grid, RT2, smem, st>>>(a);
-      else if (tune == 2) rasterize_bwd2_kernel<B2, false, 5, 4, 4><<<grid, RT2, sizeof(Smem<DP, B2, 4>), st>>>(a);
-      else rasterize_bwd2_kernel<B2, false, 5, 4, 3><<<grid, RT2, sizeof(Smem<DP, B2, 3>), st>>>(a);   // default: ring
+#define RS_BWD2(ABS_, MINB_, S_)                                                                                       \
+  do {                                                                                                                 \
+    if (a.end_dev) rasterize_bwd2_kernel<B2, ABS_, MINB_, 4, S_, true><<<grid, RT2, sizeof(Smem<DP, B2, S_>), st>>>(a); \
+    else rasterize_bwd2_kernel<B2, ABS_, MINB_, 4, S_, false><<<grid, RT2, sizeof(Smem<DP, B2, S_>), st>>>(a);         \
+  } while (0)
+      if (a.abs_grad) RS_BWD2(true, 4, 2);
+      else if (tune == 7) RS_BWD2(false, 7, 2);
+      else if (tune == 6) RS_BWD2(false, 6, 2);
+      else if (a.flags & F_BWD_BARRIER) RS_BWD2(false, 4, 2);
+      else if (tune == 2) RS_BWD2(false, 5, 4);
+      else RS_BWD2(false, 5, 3);   // default: ring
+#undef RS_BWD2
       RS_RETURN_LAST_ERROR();
     }
   }
@@ -2029,7 +2060,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
                                 const int32_t* flatten_ids, long long M, float* out_colors, float* out_alphas,
                                 float* out_expected_depths, float* out_median_depths, float* out_normals,
                                 float* out_transmittance, int32_t* last_ids, int32_t* median_ids, int flags,
-                                unsigned long long* stats, const long long* n_isects_dev, void* stream) {
+                                unsigned long long* stats, const int32_t* n_isects_dev, void* stream) {
   RsSpan span__("rs_rasterize_fwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
   RasterArgs a{};
@@ -2043,7 +2074,7 @@ extern "C" int rs_rasterize_fwd(const float* geom, const float* colors_padded, i
   a.out_colors = out_colors; a.out_alphas = out_alphas; a.out_dexp = out_expected_depths; a.out_dmed = out_median_depths;
   a.out_normals = out_normals; a.out_T = out_transmittance; a.last_ids = last_ids; a.median_ids = median_ids;
   a.stats = stats;
-  a.M_dev = n_isects_dev;
+  a.end_dev = n_isects_dev;
   if (!check_common(a) || !out_colors || !out_alphas || !out_expected_depths || !out_median_depths || !out_normals)
     return RS_ERR_BAD_ARG;
   if (ed_channel >= D) return RS_ERR_BAD_ARG;
@@ -2065,7 +2096,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
                                 const float* transmittance, const int32_t* last_ids, const int32_t* median_ids,
                                 const float* v_colors, const float* v_alphas, const float* v_expected_depths,
                                 const float* v_median_depths, const float* v_normals, float* geom_grad,
-                                float* color_grad, float* abs_grad, int flags, const long long* n_isects_dev,
+                                float* color_grad, float* abs_grad, int flags, const int32_t* n_isects_dev,
                                 void* stream) {
   RsSpan span__("rs_rasterize_bwd", stream);
   if (M >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
@@ -2081,7 +2112,7 @@ extern "C" int rs_rasterize_bwd(const float* geom, const float* colors_padded, i
   a.out_T = (float*)transmittance; a.last_ids = (int*)last_ids; a.median_ids = (int*)median_ids;
   a.v_colors = v_colors; a.v_alphas = v_alphas; a.v_dexp = v_expected_depths; a.v_dmed = v_median_depths;
   a.v_normals = v_normals; a.geom_grad = geom_grad; a.color_grad = color_grad; a.abs_grad = abs_grad;
-  a.M_dev = n_isects_dev;
+  a.end_dev = n_isects_dev;
   const int DP = padded_channels(D);
   if (!check_common(a) || !v_colors || !v_alphas || !v_expected_depths || !v_median_depths || !v_normals ||
       !geom_grad || (DP > 4 && !color_grad) || (ed_channel >= 0 && !out_colors) || ed_channel >= D)

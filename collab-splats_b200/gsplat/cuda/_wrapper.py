@@ -400,8 +400,9 @@ def isect_tiles_and_offsets(means2d: Tensor, radii: Tensor, depths: Tensor, tile
 @torch.no_grad()
 def isect_tiles_and_offsets_sync_free(means2d: Tensor, radii: Tensor, depths: Tensor, tile_width: int, tile_height: int):
     """`isect_tiles_and_offsets` without the device->host read of the intersection count (see SYNC_FREE).
-    -> tiles_per_gauss, isect_ids [capacity], flatten_ids [capacity], isect_offsets, n_isects (device i64 scalar),
-    overflow (device i32 flag); None if the capacity of this problem has not been learned yet."""
+    -> tiles_per_gauss, isect_ids [capacity], flatten_ids [capacity], isect_offsets, n_isects (device int32 [1]: the
+    number of valid list entries = min(count, capacity)), overflow (device i32 flag, raised when the count exceeded the
+    capacity), the count itself (device i64 scalar); None if the capacity of this problem has not been learned yet."""
     lib = _be.load()
     C, N = depths.shape
     dev = means2d.device
@@ -448,9 +449,10 @@ def isect_tiles_and_offsets_sync_free(means2d: Tensor, radii: Tensor, depths: Te
                                                 _be.ptr(n_isects), 32, end_bit, _be.ptr(stemp), sb, st),
                           "rs_sort_pairs_dev")
         ids, flat = (ids_b, flat_b) if where == 0 else (ids_a, flat_a)
+        n_valid = torch.empty(1, device=dev, dtype=torch.int32)     # min(count, capacity): what the compositing reads
         _be.check(lib.rs_offset_encode_dev(_be.ptr(ids), cap, _be.ptr(n_isects), C, tile_width, tile_height,
-                                           _be.ptr(offsets), st), "rs_offset_encode_dev")
-    return tiles, ids, flat, offsets, n_isects, overflow
+                                           _be.ptr(offsets), _be.ptr(n_valid), st), "rs_offset_encode_dev")
+    return tiles, ids, flat, offsets, n_valid, overflow, n_isects
 
 
 def isect_learn_capacity(device, C: int, N: int, tile_width: int, tile_height: int, n_isects: int):
@@ -670,7 +672,7 @@ def rasterize_to_pixels(
     return_ids: bool = False,
     compensations: Optional[Tensor] = None,  # [C,N]    fused: effective opacity = opacities * compensations
     ed_channel: int = -1,                    # fused "ED": that output channel is divided by max(alpha, 1e-10)
-    n_isects: Optional[Tensor] = None,       # device i64 scalar: the number of valid entries of flatten_ids (sync-free
+    n_isects: Optional[Tensor] = None,       # device int32 [1]: the number of valid entries of flatten_ids (sync-free
                                              # callers, whose buffers are capacity-sized); None = all of them
 ):
     """gsplat ``rasterize_to_pixels`` + the RaDe outputs.  Returns ``(colors [C,H,W,D], alphas [C,H,W,1])``

@@ -123,10 +123,10 @@ def rasterization(
     # ---- tile intersection, sort, offsets
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
-    n_isects = overflow = None
+    n_isects = overflow = n_total = None
     sf = _W.isect_tiles_and_offsets_sync_free(means2d, radii, depths, tile_width, tile_height) if _W.SYNC_FREE else None
     if sf is not None:      # no device->host read: capacity-sized lists, the count stays on the device
-        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets, n_isects, overflow = sf
+        tiles_per_gauss, isect_ids, flatten_ids, isect_offsets, n_isects, overflow, n_total = sf
     else:
         tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
             means2d, radii, depths, tile_size, tile_width, tile_height)
@@ -168,7 +168,7 @@ def rasterization(
         "tile_width": tile_width, "tile_height": tile_height, "tiles_per_gauss": tiles_per_gauss,
         "isect_ids": isect_ids, "flatten_ids": flatten_ids, "isect_offsets": isect_offsets, "width": width,
         "height": height, "tile_size": tile_size, "n_cameras": C,
-        "n_isects": n_isects if n_isects is not None else flatten_ids.numel(), "isect_overflow": overflow,
+        "n_isects": n_total if n_total is not None else flatten_ids.numel(), "isect_overflow": overflow,
     }
     if return_depth_normal:
         return render_colors, render_alphas, exp_d, med_d, nrm, meta

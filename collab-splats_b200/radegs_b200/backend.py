@@ -56,7 +56,7 @@ _SIGNATURES = {
                          + [_p, _p, _p] + [_i, _p, _p]),
     "rs_isect_emit_ordered_bounded": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _ll, _p, _p]),
     "rs_sort_pairs_dev": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _p, _ll, _p]),
-    "rs_offset_encode_dev": (_i, [_p, _ll, _p, _i, _i, _i, _p, _p]),
+    "rs_offset_encode_dev": (_i, [_p, _ll, _p, _i, _i, _i, _p, _p, _p]),
     "rs_unpack_geom_grad": (_i, [_p, _p, _p, _i, _i, _p, _i, _p] + [_p] * 9 + [_i, _i, _p]),
     "rs_sh_colors_fwd": (_i, [_i, _i, _i, _i] + [_p] * 6 + [_p]),
     "rs_sh_colors_bwd": (_i, [_i, _i, _i, _i] + [_p] * 5 + [_i] + [_p] * 3 + [_p]),

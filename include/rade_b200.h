@@ -146,7 +146,7 @@ int rs_rasterize_fwd(const float* geom, const float* colors_padded, int color_pe
                      long long M, float* out_colors /* [C,H,W,D] */, float* out_alphas /* [C,H,W] */,
                      float* out_expected_depths, float* out_median_depths, float* out_normals /* [C,H,W,3] */,
                      float* out_transmittance, int32_t* last_ids, int32_t* median_ids, int flags,
-                     unsigned long long* stats, const long long* n_isects_dev /* NULL, or see below */, void* stream);
+                     unsigned long long* stats, const int32_t* n_valid_dev /* NULL, or see below */, void* stream);
 /* Gradient record geom_grad[C*N,16] = (S v_sigma*dx, S v_sigma*dy | ga gb gc | S v_sigma | g_ray_t g_rpx g_rpy |
  * gnx gny gnz | colour 0..3), S = sum over blended pixels; rs_unpack_geom_grad turns the three moments into the
  * means2d and opacity gradients (per-Gaussian linear maps with the conic / ray plane / opacity of `geom`);
@@ -159,14 +159,15 @@ int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_pe
                      const int32_t* median_ids, const float* v_colors, const float* v_alphas,
                      const float* v_expected_depths, const float* v_median_depths, const float* v_normals,
                      float* geom_grad, float* color_grad, float* abs_grad, int flags,
-                     const long long* n_isects_dev /* NULL, or see below */, void* stream);
+                     const int32_t* n_valid_dev /* NULL, or see below */, void* stream);
 
 /* ---- sync-free intersections: the number of intersections M never travels to the host.  The caller sizes isect_ids /
  * flatten_ids (and the sort's temp) for a CAPACITY learned from an earlier step, passes the device address of the count
  * (the last element of the inclusive scan) and gets an overflow flag instead of a short buffer: entries past the
  * capacity are dropped and *overflow is raised (check it off the hot path, re-run with a larger capacity).  With these
  * entry points a whole training step contains no device->host read and can be captured in a CUDA graph.
- * rs_rasterize_fwd / rs_rasterize_bwd take the same device count as n_isects_dev (M = the capacity). */
+ * rs_offset_encode_dev also writes *n_valid = min(count, capacity) (int32); rs_rasterize_fwd / rs_rasterize_bwd take
+ * that word as n_valid_dev (their M is then the capacity). */
 int rs_isect_emit_ordered_bounded(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
                                   const long long* cum_tiles, int C, int N, int tile_w, int tile_h, long long* isect_ids,
                                   int32_t* flatten_ids, long long capacity, int32_t* overflow, void* stream);
@@ -174,7 +175,7 @@ int rs_sort_pairs_dev(long long* keys_a, int32_t* vals_a, long long* keys_b, int
                       const long long* n_pairs_dev, int begin_bit, int end_bit, void* temp, long long temp_bytes,
                       void* stream);
 int rs_offset_encode_dev(const long long* isect_ids, long long capacity, const long long* n_isects_dev, int C, int tile_w,
-                         int tile_h, int32_t* offsets, void* stream);
+                         int tile_h, int32_t* offsets, int32_t* n_valid, void* stream);
 /* Splits the gradient record into the per-input gradients; undoes the opacity * compensation fusion
  * (v_compensations[C,N] = go * opacity, v_opacities = go * compensation, summed over cameras when the
  * opacities are [N]); v_colors4 (NULL ok) receives the colour gradient when the colours have <= 4 channels. */

@@ -1,6 +1,7 @@
 #!/bin/bash
-# Round-2 evidence run on one B200: GPU tests (with the gradient-parity report), smoke, bench N=1 (both arms), the ncu
-# launch list of one resident step and the full capture of the compositing kernels.  Logs to gpurun_out/r2_*.
+# Round-2 evidence run on one B200, part A: GPU tests (with the gradient-parity report), smoke, bench N=1 (both arms) and
+# the ncu launch list of one resident step.  Part B (scripts/gpu_round2_ncu.sh) is the full ncu capture: one profiler
+# tool per gpurun call.  Logs to gpurun_out/r2_*.
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -s > gpurun_out/r2_pytest_full.log 2>&1; echo "pytest exit $?"
 tail -4 gpurun_out/r2_pytest_full.log
@@ -12,9 +13,4 @@ $CMD > gpurun_out/r2_profile_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/r2_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-$CMD > gpurun_out/r2_profile_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k 'regex:rasterize_|radix_scatter|radix_hist|project_|sh_colors|isect_|scan_kernel|pack_geom|unpack_geom|rade_loss|offset_encode' \
-    -o gpurun_out/r2_prof_step -f $CMD > gpurun_out/r2_ncu_full.log 2>&1
-echo "ncu full exit $?"
 head -c 1500 gpurun_out/r2_bench_n1.json; echo; head -c 1200 gpurun_out/r2_bench_ref.json
