@@ -708,6 +708,7 @@ def multi_gpu_diagnostics(wl, world, device, lib, backend, resident, push_engine
             "main_stream_phases_ms_rank0": {k: round(v, 4) for k, v in tail.items()},
             "n_isects_per_rank": [int(v[1]) for v in everyone],
             "exchange_spans_ms_rank0": {k: round(spans[k][0] / 5, 4) for k in keys if k in spans},
+            "stage_ms_with_exchange_rank0": {k: round(v[0] / 5, 4) for k, v in sorted(spans.items(), key=lambda kv: -kv[1][0])},
             "grad_exchange": wl.exchange_mode + ("/" + push_engine if wl.exchange_mode == "push" else ""),
             "note": "step time = slowest rank's compute + exposed exchange; rs_peer_wait is time spent waiting "
                     "for the slowest peer's colour gradients"}
