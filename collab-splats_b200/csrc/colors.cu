@@ -194,14 +194,15 @@ sh_colors_bwd_kernel(int degree, int K, int C, int N, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------ camera-sharded split
 // Multi-GPU (camera-sharded) form of the backward.  The SH-coefficient gradient of one camera is the outer product
 // Y_k(dir(n, camera)) x v_rgb[n]: 48 floats per Gaussian that carry 3 floats of information.  So instead of
-// all-reducing 192 B per Gaussian, every rank publishes its masked colour gradients (16 B per Gaussian and camera)
+// all-reducing 192 B per Gaussian, every rank publishes its masked colour gradients (12 B per Gaussian and camera)
 // in peer-visible memory and every rank rebuilds the SUM OVER ALL CAMERAS OF ALL RANKS of the outer products
 // itself, reading the other ranks' rows straight over NVLink (or from an all-gathered copy):
-//   sh_colors_bwd_local_kernel : v_colors4 -> vrgb[C,N] (float4: clamp/visibility-masked rgb gradient, w = 0),
+//   sh_colors_bwd_local_kernel : v_colors4 -> vrgb[C,N,3] (clamp/visibility-masked rgb gradient),
 //                                v_means (direction part), v_depths; also writes the camera positions to the header
 //   sh_coeffs_gather_kernel    : v_coeffs[n,k,:] = sum over sources (rank g, camera c) of Y_k(dir(n, campos_gc)) *
 //                                vrgb_gc[n,:], in a fixed (g, c) order, so every rank gets bit-identical sums.
-// A source region is [header: RS_PEER_HEADER_BYTES, float4 campos per camera][float4 vrgb[cams][N]].
+// A source region is [header: RS_PEER_HEADER_BYTES, float4 campos per camera][float vrgb[cams][N][3]] -- 12 B per Gaussian
+// and camera (round 2: was a padded float4; at 8 GPUs the pushes are NVLink-bandwidth-bound, a quarter fewer bytes).
 constexpr int RS_PEER_HEADER_BYTES = 1024;  // up to 64 cameras per rank
 constexpr int RS_MAX_PEERS = 16;
 constexpr int RS_MAX_SOURCES = 64;   // cameras of all ranks in one step
@@ -232,7 +233,7 @@ sh_colors_bwd_local_kernel(int degree, int K, int C, int N, const float* __restr
   if (t >= count) return;
   const int nb = (degree + 1) * (degree + 1);
   const int n = n0 + t;
-  float4* vrgb = reinterpret_cast<float4*>(region + RS_PEER_HEADER_BYTES);
+  float* vrgb = reinterpret_cast<float*>(region + RS_PEER_HEADER_BYTES);
   float vmx = 0.f, vmy = 0.f, vmz = 0.f;
   const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
   const float* cf = s_rows + t * RS;
@@ -255,7 +256,7 @@ sh_colors_bwd_local_kernel(int degree, int K, int C, int N, const float* __restr
       if (q < nb) { r += basis[q] * cf[q * 3]; g += basis[q] * cf[q * 3 + 1]; b += basis[q] * cf[q * 3 + 2]; }
     const float vr = (live && r + 0.5f >= 0.f) ? vc.x : 0.f, vg = (live && g + 0.5f >= 0.f) ? vc.y : 0.f,
                 vb = (live && b + 0.5f >= 0.f) ? vc.z : 0.f;
-    vrgb[e] = make_float4(vr, vg, vb, 0.f);
+    vrgb[e * 3] = vr; vrgb[e * 3 + 1] = vg; vrgb[e * 3 + 2] = vb;
 #pragma unroll
     for (int q = 0; q < 16; ++q) gq[q] = q < nb ? vr * cf[q * 3] + vg * cf[q * 3 + 1] + vb * cf[q * 3 + 2] : 0.f;
     float bx, by, bz;
@@ -272,7 +273,7 @@ sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ mean
                         float* __restrict__ v_coeffs) {
   extern __shared__ float s_rows[];
   __shared__ float4 s_campos[RS_MAX_SOURCES];
-  __shared__ const float4* s_rowptr[RS_MAX_SOURCES];
+  __shared__ const float* s_rowptr[RS_MAX_SOURCES];
   __shared__ int s_total;
   const int t = threadIdx.x;
   const int n0 = blockIdx.x * CB;
@@ -284,7 +285,7 @@ sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ mean
     int k = 0;
     for (int g = 0; g < src.n; ++g)
       for (int c = 0; c < src.cams[g] && k < RS_MAX_SOURCES; ++c, ++k)
-        s_rowptr[k] = reinterpret_cast<const float4*>(src.base[g] + RS_PEER_HEADER_BYTES) + (size_t)c * N;
+        s_rowptr[k] = reinterpret_cast<const float*>(src.base[g] + RS_PEER_HEADER_BYTES) + (size_t)c * N * 3;
     s_total = k;
   }
   __syncthreads();
@@ -301,12 +302,17 @@ sh_coeffs_gather_kernel(int degree, int K, int N, const float* __restrict__ mean
   const int n = n0 + t;
   if (t < count) {
     const float mx = __ldg(means + n * 3), my = __ldg(means + n * 3 + 1), mz = __ldg(means + n * 3 + 2);
-    // W (possibly remote) 16-byte loads in flight per thread before any is consumed
+    // W (possibly remote) 12-byte rows in flight per thread before any is consumed
     for (int k0 = 0; k0 < total; k0 += W) {
-      float4 v[W];
+      float3 v[W];
 #pragma unroll
-      for (int i = 0; i < W; ++i)
-        v[i] = (k0 + i < total) ? __ldcg(s_rowptr[k0 + i] + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < W; ++i) {
+        v[i] = make_float3(0.f, 0.f, 0.f);
+        if (k0 + i < total) {
+          const float* r = s_rowptr[k0 + i] + (size_t)n * 3;
+          v[i] = make_float3(__ldcg(r), __ldcg(r + 1), __ldcg(r + 2));
+        }
+      }
 #pragma unroll
       for (int i = 0; i < W; ++i) {
         if (v[i].x == 0.f && v[i].y == 0.f && v[i].z == 0.f) continue;   // culled / clamped: exact zeros
@@ -374,7 +380,8 @@ extern "C" int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* me
 // ---- camera-sharded split of rs_sh_colors_bwd (see the kernels above).  `region` is the caller's peer-visible
 // buffer of rs_sh_region_bytes(C, N) bytes; v_coeffs is NOT produced here but by rs_sh_coeffs_gather on every rank.
 extern "C" long long rs_sh_region_bytes(int C, int N) {
-  return (long long)RS_PEER_HEADER_BYTES + 16ll * (long long)(C > 0 ? C : 0) * (long long)(N > 0 ? N : 0);
+  const long long rows = 12ll * (long long)(C > 0 ? C : 0) * (long long)(N > 0 ? N : 0);
+  return (long long)RS_PEER_HEADER_BYTES + (rows + 15) / 16 * 16;
 }
 
 extern "C" int rs_sh_colors_bwd_local(int degree, int K, int C, int N, const float* means, const float* coeffs,

@@ -90,10 +90,10 @@ class ShGradExchange:
     """SH-coefficient gradients for the camera-sharded step WITHOUT all-reducing them (csrc/colors.cu, csrc/peer.cu).
 
     The coefficient gradient of one camera is the outer product ``Y_k(dir(n, camera)) x v_rgb[n]``: 48 floats per
-    Gaussian that carry 3.  Each rank therefore publishes its clamp/visibility-masked colour gradients (16 B per
+    Gaussian that carry 3.  Each rank therefore publishes its clamp/visibility-masked colour gradients (12 B per
     Gaussian and camera) and every rank rebuilds the sum over the cameras of ALL ranks with one kernel
     (``rs_sh_coeffs_gather``), in a fixed (rank, camera) order, so all replicas hold bit-identical gradients.  At sh3
-    this replaces a 192 B/Gaussian all-reduce (ring traffic 2(G-1)/G x 192 B) by (G-1) x 16 B/Gaussian of reads.
+    this replaces a 192 B/Gaussian all-reduce (ring traffic 2(G-1)/G x 192 B) by (G-1) x 12 B/Gaussian of reads.
 
     ``mode="push"`` (default): every rank owns an inbox per rank in CUDA-IPC-shared device memory; right after the
     colour backward a rank copies its region into its slot of every peer's inbox with the COPY ENGINES (no SMs), on

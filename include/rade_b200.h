@@ -199,10 +199,10 @@ int rs_sh_colors_bwd(int degree, int K, int C, int N, const float* means, const 
 
 /* ---- camera-sharded multi-GPU form of rs_sh_colors_bwd (Gaussians replicated, cameras sharded).
  * The SH-coefficient gradient of one camera is Y_k(dir) x v_rgb (48 floats carrying 3), so instead of all-reducing
- * 192 B per Gaussian each rank publishes its masked colour gradients (16 B per Gaussian and camera) in a
+ * 192 B per Gaussian each rank publishes its masked colour gradients (12 B per Gaussian and camera) in a
  * peer-visible `region` and every rank rebuilds the sum over ALL cameras of ALL ranks itself, reading the other
  * ranks' regions over NVLink (regions[] = peer-mapped pointers) or from an all-gathered copy.
- * region layout: [1024 B header: float4 camera position per camera][float4 vrgb[C][N]], rs_sh_region_bytes(C, N). */
+ * region layout: [1024 B header: float4 camera position per camera][float vrgb[C][N][3]] rounded up to 16 B, rs_sh_region_bytes(C, N). */
 long long rs_sh_region_bytes(int C, int N);
 int rs_sh_colors_bwd_local(int degree, int K, int C, int N, const float* means, const float* coeffs,
                            const float* viewmats, const int32_t* radii, const float* v_colors4, int has_depth,

@@ -13,8 +13,8 @@ regions = []
 for s in range(S):
     r = torch.zeros(lib.rs_sh_region_bytes(1, N), device=dev, dtype=torch.uint8)
     r[:16].view(torch.float32)[:4] = torch.tensor([3.0 * (s + 1), 0.1 * s, -2.0, 1.0], device=dev)
-    body = r[1024:1024 + N * 16].view(torch.float32).view(N, 4)
-    body[:, :3] = torch.randn(N, 3, device=dev) * (torch.rand(N, 1, device=dev) > 0.2)
+    body = r[1024:1024 + N * 12].view(torch.float32).view(N, 3)
+    body[:] = torch.randn(N, 3, device=dev) * (torch.rand(N, 1, device=dev) > 0.2)
     regions.append(r)
 v = torch.empty(N, K, 3, device=dev)
 ptrs = (ct.c_void_p * S)(*[r.data_ptr() for r in regions]); cams = (ct.c_int * S)(*[1] * S)
@@ -27,4 +27,4 @@ for _ in range(10):
     e0.record(); be.check(lib.rs_sh_coeffs_gather(3, K, N, be.ptr(means), ptrs, cams, S, be.ptr(v), st), "g"); e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ts.sort()
-print(f"sources {S}: gather median {ts[5]:.4f} ms, {(N * (16 * S + 12 + 192)) / (ts[5] * 1e-3) / 1e9:.0f} GB/s algorithmic; checksum {float(v.sum()):.3f}")
+print(f"sources {S}: gather median {ts[5]:.4f} ms, {(N * (12 * S + 12 + 192)) / (ts[5] * 1e-3) / 1e9:.0f} GB/s algorithmic; checksum {float(v.sum()):.3f}")
