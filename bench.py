@@ -825,6 +825,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)       # (torchrun exports OMP_NUM_THREADS=1 to its workers: undo that for this arm)
     budget_s = 150.0
     t_start = time.perf_counter()
     keep, times = None, []
