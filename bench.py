@@ -393,8 +393,7 @@ def graph_replay_block(wl, steps, device):
         for k, v in wl.params.items():
             worst = max(worst, float((v.grad - ref[k]).abs().max() / (ref[k].abs().max() + 1e-30)))
         out["max_rel_grad_diff_vs_eager"] = worst
-        (cap, _), = W._ISECT_CAPACITY.values()
-        out["isect_capacity"] = int(cap)
+        out["isect_capacity"] = int(next(iter(W._ISECT_CAPACITY.values()))[0])
         out["what"] = ("fwd + fused loss + bwd of the headline step; intersection buffers sized for 1.25x the count learned "
                        "on the first step, count read by the kernels from device memory, overflow flag checked after")
         del graph

@@ -178,7 +178,7 @@ isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __rest
                           const float* __restrict__ depths, const int32_t* __restrict__ order,
                           const long long* __restrict__ cum, int C, int N, int tile_w, int tile_h, int tile_bits,
                           long long* __restrict__ isect_ids, int32_t* __restrict__ flatten_ids, long long capacity,
-                          int* __restrict__ overflow) {
+                          int* __restrict__ overflow, long long* __restrict__ count_mirror = nullptr) {
   constexpr int WARPS = IB / 32;
   __shared__ int s_pref[WARPS][33];
   __shared__ int s_xmin[WARPS][32], s_ymin[WARPS][32], s_w[WARPS][32], s_e[WARPS][32];
@@ -194,7 +194,10 @@ isect_emit_ordered_kernel(const float2* __restrict__ means2d, const int2* __rest
     if (tile_bbox(__ldg(means2d + e), __ldg(radii + e), tile_w, tile_h, xmin, ymin, xmax, ymax))
       cnt = max((xmax - xmin) * (ymax - ymin), 0);
     // bounded output (capacity-sized buffers, device-side count): the last entry knows the total
-    if (p == total - 1 && overflow && cum_p > capacity) *overflow = 1;
+    if (p == total - 1) {
+      if (overflow && cum_p > capacity) *overflow = 1;
+      if (count_mirror) *count_mirror = cum_p;   // (may be mapped host memory: read by the host a step later, no sync)
+    }
   }
   int incl = cnt;   // inclusive prefix of the counts inside the warp
 #pragma unroll
@@ -451,7 +454,7 @@ extern "C" int rs_isect_emit_ordered(const float* means2d, const int32_t* radii,
 extern "C" int rs_isect_emit_ordered_bounded(const float* means2d, const int32_t* radii, const float* depths,
                                              const int32_t* order, const long long* cum_tiles, int C, int N, int tile_w,
                                              int tile_h, long long* isect_ids, int32_t* flatten_ids, long long capacity,
-                                             int32_t* overflow, void* stream) {
+                                             int32_t* overflow, long long* count_mirror, void* stream) {
   RsSpan span__("rs_isect_emit_ordered", stream);
   if (C < 0 || N < 0 || tile_w <= 0 || tile_h <= 0 || capacity <= 0) return RS_ERR_BAD_ARG;
   if ((long long)C * N >= (1ll << 31) || capacity >= (1ll << 31)) return RS_ERR_UNSUPPORTED;
@@ -461,7 +464,7 @@ extern "C" int rs_isect_emit_ordered_bounded(const float* means2d, const int32_t
   int tile_bits = tile_bits_for((long long)tile_w * tile_h);
   isect_emit_ordered_kernel<<<rs_div_up((long long)C * N, IB), IB, 0, (cudaStream_t)stream>>>(
       (const float2*)means2d, (const int2*)radii, depths, order, cum_tiles, C, N, tile_w, tile_h, tile_bits, isect_ids,
-      flatten_ids, capacity, overflow);
+      flatten_ids, capacity, overflow, count_mirror);
   RS_RETURN_LAST_ERROR();
 }
 

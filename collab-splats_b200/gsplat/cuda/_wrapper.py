@@ -13,8 +13,10 @@ collab-splats never uses (packed=True, sparse_grad, covars, non-pinhole cameras,
 
 from __future__ import annotations
 
+import ctypes
 import math
 import os
+import warnings
 from typing import Optional, Tuple
 
 import torch
@@ -47,14 +49,21 @@ RASTER_STATS = None
 # path with `isect_overflowed()`) if a step ever produced more intersections than the capacity.
 SYNC_FREE = False
 ISECT_HEADROOM = 1.25
-_ISECT_CAPACITY = {}      # (device index, C, N, tile_w, tile_h) -> [capacity, overflow flag tensor]
+# One step late and without a synchronisation the host still follows the count: the emit kernel mirrors it into a word of
+# pinned host memory, which the next render of the same problem reads as plain host memory.  With ISECT_AUTO_GROW the
+# capacity then follows the largest count seen (x ISECT_HEADROOM) -- views with more intersections than the first one
+# grow the buffers before they overflow, as long as the count does not jump by more than the headroom between two
+# consecutive renders -- and a render that did overflow is reported with a warning on the next call.  (Not under CUDA
+# graph capture, where Python does not run per replay: check `isect_overflowed()` there.)
+ISECT_AUTO_GROW = True
+_ISECT_CAPACITY = {}      # (device index, C, N, tile_w, tile_h) -> [capacity, overflow flag (device), count mirror (pinned host)]
 
 
 def isect_overflowed(reset: bool = True) -> bool:
     """True if any sync-free call since the last check dropped intersections (device->host read: off the hot path).
     The capacities of the problems that overflowed are forgotten, so their next call re-learns them."""
     bad = False
-    for key, (cap, flag) in list(_ISECT_CAPACITY.items()):
+    for key, (cap, flag, _mirror) in list(_ISECT_CAPACITY.items()):
         if int(flag.item()) != 0:
             bad = True
             if reset:
@@ -409,7 +418,17 @@ def isect_tiles_and_offsets_sync_free(means2d: Tensor, radii: Tensor, depths: Te
     key = (dev.index, C, N, tile_width, tile_height)
     if key not in _ISECT_CAPACITY or C * N == 0:
         return None
-    cap, overflow = _ISECT_CAPACITY[key]
+    entry = _ISECT_CAPACITY[key]
+    cap, overflow, mirror = entry
+    if ISECT_AUTO_GROW and not torch.cuda.is_current_stream_capturing():
+        last = int(mirror[0])                  # the count of an earlier render of this problem: host memory, no sync
+        if last > cap:
+            warnings.warn(f"sync-free intersections: an earlier render of this problem produced {last} intersections "
+                          f"for a capacity of {cap} and was truncated; the capacity has been raised "
+                          "(raise gsplat.cuda._wrapper.ISECT_HEADROOM if views differ this much)")
+        want = (int(last * ISECT_HEADROOM) + 4096 + 2047) // 2048 * 2048
+        if last > 0 and want > cap:
+            cap = entry[0] = want
     means2d, depths = _c(means2d), _c(depths)
     radii = _c(radii, torch.int32)
     n_elems = C * N
@@ -441,7 +460,8 @@ def isect_tiles_and_offsets_sync_free(means2d: Tensor, radii: Tensor, depths: Te
         ids_b, flat_b = torch.empty_like(ids_a), torch.empty_like(flat_a)
         _be.check(lib.rs_isect_emit_ordered_bounded(_be.ptr(means2d), _be.ptr(radii), _be.ptr(depths), _be.ptr(order),
                                                     _be.ptr(cum), C, N, tile_width, tile_height, _be.ptr(ids_a),
-                                                    _be.ptr(flat_a), cap, _be.ptr(overflow), st),
+                                                    _be.ptr(flat_a), cap, _be.ptr(overflow),
+                                                    ctypes.c_void_p(mirror.data_ptr()), st),
                   "rs_isect_emit_ordered_bounded")
         sb = lib.rs_sort_pairs_temp_bytes(cap, 32, end_bit)
         stemp = torch.empty(sb, device=dev, dtype=torch.uint8)
@@ -461,7 +481,8 @@ def isect_learn_capacity(device, C: int, N: int, tile_width: int, tile_height: i
     key = (device.index, C, N, tile_width, tile_height)
     cap = max(int(n_isects * ISECT_HEADROOM) + 4096, 4096)
     cap = (cap + 2047) // 2048 * 2048
-    _ISECT_CAPACITY[key] = [cap, torch.zeros(1, device=device, dtype=torch.int32)]
+    _ISECT_CAPACITY[key] = [cap, torch.zeros(1, device=device, dtype=torch.int32),
+                            torch.zeros(1, dtype=torch.int64).pin_memory()]
 
 
 @torch.no_grad()

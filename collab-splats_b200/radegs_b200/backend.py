@@ -54,7 +54,7 @@ _SIGNATURES = {
     "rs_rasterize_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 8 + [_i, _p, _p, _p]),
     "rs_rasterize_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p] + [_i] * 6 + [_p, _p, _ll] + [_p] * 4 + [_p] * 5
                          + [_p, _p, _p] + [_i, _p, _p]),
-    "rs_isect_emit_ordered_bounded": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _ll, _p, _p]),
+    "rs_isect_emit_ordered_bounded": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _ll, _p, _p, _p]),
     "rs_sort_pairs_dev": (_i, [_p, _p, _p, _p, _ll, _p, _i, _i, _p, _ll, _p]),
     "rs_offset_encode_dev": (_i, [_p, _ll, _p, _i, _i, _i, _p, _p, _p]),
     "rs_unpack_geom_grad": (_i, [_p, _p, _p, _i, _i, _p, _i, _p] + [_p] * 9 + [_i, _i, _p]),

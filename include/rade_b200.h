@@ -170,7 +170,10 @@ int rs_rasterize_bwd(const float* geom, const float* colors_padded, int color_pe
  * that word as n_valid_dev (their M is then the capacity). */
 int rs_isect_emit_ordered_bounded(const float* means2d, const int32_t* radii, const float* depths, const int32_t* order,
                                   const long long* cum_tiles, int C, int N, int tile_w, int tile_h, long long* isect_ids,
-                                  int32_t* flatten_ids, long long capacity, int32_t* overflow, void* stream);
+                                  int32_t* flatten_ids, long long capacity, int32_t* overflow,
+                                  long long* count_mirror /* NULL, or any device-visible word (e.g. mapped pinned
+                                  host memory) that receives the count: lets the host follow it one step late */,
+                                  void* stream);
 int rs_sort_pairs_dev(long long* keys_a, int32_t* vals_a, long long* keys_b, int32_t* vals_b, long long capacity,
                       const long long* n_pairs_dev, int begin_bit, int end_bit, void* temp, long long temp_bytes,
                       void* stream);

@@ -15,11 +15,11 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture
 def sync_free():
     from gsplat.cuda import _wrapper as W
-    old = (W.SYNC_FREE, W.ISECT_HEADROOM)
+    old = (W.SYNC_FREE, W.ISECT_HEADROOM, W.ISECT_AUTO_GROW)
     W._ISECT_CAPACITY.clear()
     W.SYNC_FREE = True
     yield W
-    W.SYNC_FREE, W.ISECT_HEADROOM = old
+    W.SYNC_FREE, W.ISECT_HEADROOM, W.ISECT_AUTO_GROW = old
     W._ISECT_CAPACITY.clear()
 
 
@@ -76,6 +76,7 @@ def test_sync_free_overflow_is_flagged_not_fatal(cuda_dev, sync_free):
     cap = entry[0] = 2048 * (first[5]["n_isects"] // 4096)          # pretend a far too small capacity was learned
     assert cap >= 2048
     del first
+    sync_free.ISECT_AUTO_GROW = False                               # (the automatic growth has its own test below)
     p = _leaves(gs, cuda_dev)
     out = _call(p, vm, Ks, 160, 96)
     _loss(out).backward()                                           # truncated lists: wrong image, but no fault
@@ -91,6 +92,43 @@ def test_sync_free_overflow_is_flagged_not_fatal(cuda_dev, sync_free):
     _call(_leaves(gs, cuda_dev), vm, Ks, 160, 96)
     again = _call(_leaves(gs, cuda_dev), vm, Ks, 160, 96)
     assert int(again[5]["isect_overflow"]) == 0
+
+
+def test_sync_free_capacity_follows_the_count_one_step_late(cuda_dev, sync_free):
+    """Views with more intersections than the first one: the emit kernel mirrors the count into pinned host memory, the
+    next render reads it (no synchronisation) and grows the buffers; a render that overflowed is reported then."""
+    import warnings
+    cfg, gs, vm, Ks = small_scene(n=4000, w=160, h=96)
+    vm, Ks = vm.to(cuda_dev), Ks.to(cuda_dev)
+
+    def render(boost):
+        g2 = dict(gs)
+        g2["log_scales"] = gs["log_scales"] + boost
+        return _call(_leaves(g2, cuda_dev), vm, Ks, 160, 96)
+
+    m0 = render(0.0)[5]["n_isects"]                                 # learns the capacity (synchronising call)
+    (entry,) = sync_free._ISECT_CAPACITY.values()
+    cap0 = entry[0] = (int(m0 * 1.1) + 2047) // 2048 * 2048         # (small scene: drop the constant part of the headroom)
+    out = render(0.02)                                              # a few more intersections: fits, mirrored
+    torch.cuda.synchronize()
+    m1 = int(entry[2][0])
+    assert m1 == int(out[5]["n_isects"]) and m0 < m1 <= cap0 and int(out[5]["isect_overflow"]) == 0
+    big = render(1.5)                                               # far more than the headroom: truncated ...
+    torch.cuda.synchronize()
+    assert int(entry[2][0]) > cap0 and int(big[5]["isect_overflow"]) == 1
+    assert entry[0] >= cap0                                         # (may already have grown for m1)
+    cap0 = entry[0]
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        again = render(1.5)                                         # ... reported and repaired on the next call
+    assert any("truncated" in str(w.message) for w in caught)
+    assert entry[0] > cap0 and again[5]["flatten_ids"].numel() == entry[0]
+    sync_free.SYNC_FREE = False
+    ref = render(1.5)
+    M = ref[5]["flatten_ids"].numel()
+    assert torch.equal(again[5]["flatten_ids"][:M], ref[5]["flatten_ids"])
+    for a, b in zip(again[:5], ref[:5]):
+        assert torch.equal(a, b)
 
 
 def test_sync_free_nothing_visible(cuda_dev, sync_free):
