@@ -210,8 +210,8 @@ class Workload:
         self.copy_stream = torch.cuda.Stream(self.device)
         self.in_bufs = [dict(vm=torch.empty_like(self.viewmat), K=torch.empty_like(self.K), gt=torch.empty_like(self.gt),
                              ev=torch.cuda.Event()) for _ in range(2)]
-        self.loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
-        self.loss_ev = [None, None]
+        self.loss_host = [torch.zeros(1).pin_memory() for _ in range(self.LOSS_LAG + 1)]
+        self.loss_ev = [None] * (self.LOSS_LAG + 1)
         self.e2e_i = 0
         self._prefetch(0)
 
@@ -237,18 +237,23 @@ class Workload:
         self.backward(loss)
         return loss
 
+    LOSS_LAG = 2   # the loss of step i is read on the host while step i + LOSS_LAG is being queued (a logger's view)
+
     def read_loss_async(self, loss):
-        """Queue the D2H copy of this step's loss; return the previous step's value (already on the host)."""
+        """Queue the D2H copy of this step's loss (every step); return the value of the step LOSS_LAG steps back, which
+        has landed in pinned memory by now -- the host stays at most LOSS_LAG steps ahead of the GPU, so a host hiccup
+        shorter than that much GPU work does not drain the queue."""
+        n = self.LOSS_LAG + 1
         i = self.e2e_i - 1
-        self.loss_host[i & 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        self.loss_host[i % n].copy_(loss.detach().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        self.loss_ev[i & 1] = ev
-        prev = self.loss_ev[(i + 1) & 1]
+        self.loss_ev[i % n] = ev
+        prev = self.loss_ev[(i + 1) % n]
         if prev is None:
             return None
         prev.synchronize()
-        return float(self.loss_host[(i + 1) & 1][0])
+        return float(self.loss_host[(i + 1) % n][0])
 
     # ---- multi-GPU gradient exchange.  The SH coefficients are 192 of the 236 B of gradient per Gaussian, and one
     # camera's coefficient gradient is an outer product Y_k(dir) x v_rgb, so they are NOT all-reduced: every rank
@@ -987,7 +992,7 @@ def main():
                    "loss": "L1 + depth-normal consistency (lambda 0.05, ratio 0.6); the reference's rgb term is "
                            "0.8*L1 + 0.2*(1-SSIM) from nerfstudio (rade_gs_model.py:289) -- SSIM is host-framework code "
                            "outside the path and is NOT in the timed step",
-                   "e2e_pipeline": "next step's H2D on a copy stream; loss D2H read one step later (pinned)", "n_isects": int(wl.last_meta["n_isects"]),
+                   "e2e_pipeline": "next step's H2D on a copy stream; every step's loss copied D2H (pinned) and read two steps later", "n_isects": int(wl.last_meta["n_isects"]),
                    "sync_free_intersections": bool(sync_free)},
         "clocks": clocks.summary(),
         "e2e": {"value": value_e2e, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": wl.d2h_bytes,
