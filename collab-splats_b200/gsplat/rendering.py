@@ -50,11 +50,15 @@ def rasterization(
     camera_model: str = "pinhole",
     covars: Optional[Tensor] = None,
     return_depth_normal: bool = False,
+    sync_free: Optional[bool] = None,
     **unsupported,
 ):
     """Returns ``(render_colors [C,H,W,D'], render_alphas [C,H,W,1], meta)`` or, with
     ``return_depth_normal=True`` (how the reference calls it), ``(render_colors, render_alphas,
-    expected_depths [C,H,W,1], median_depths [C,H,W,1], expected_normals [C,H,W,3], meta)``."""
+    expected_depths [C,H,W,1], median_depths [C,H,W,1], expected_normals [C,H,W,3], meta)``.
+
+    ``sync_free`` (not an upstream argument; None = ``gsplat.cuda._wrapper.SYNC_FREE``, default False): never read the
+    number of intersections back to the host after the first render of a problem -- see ``_wrapper.SYNC_FREE``."""
     if unsupported:
         raise NotImplementedError(f"options not on the collab-splats path: {sorted(unsupported)}")
     if packed:
@@ -124,13 +128,14 @@ def rasterization(
     tile_width = math.ceil(width / float(tile_size))
     tile_height = math.ceil(height / float(tile_size))
     n_isects = overflow = n_total = None
-    sf = _W.isect_tiles_and_offsets_sync_free(means2d, radii, depths, tile_width, tile_height) if _W.SYNC_FREE else None
+    sync_free = _W.SYNC_FREE if sync_free is None else bool(sync_free)
+    sf = _W.isect_tiles_and_offsets_sync_free(means2d, radii, depths, tile_width, tile_height) if sync_free else None
     if sf is not None:      # no device->host read: capacity-sized lists, the count stays on the device
         tiles_per_gauss, isect_ids, flatten_ids, isect_offsets, n_isects, overflow, n_total = sf
     else:
         tiles_per_gauss, isect_ids, flatten_ids, isect_offsets = isect_tiles_and_offsets(
             means2d, radii, depths, tile_size, tile_width, tile_height)
-        if _W.SYNC_FREE:    # first call of this problem: remember how many intersections it has
+        if sync_free:       # first call of this problem: remember how many intersections it has
             _W.isect_learn_capacity(means2d.device, C, N, tile_width, tile_height, flatten_ids.numel())
 
     # ---- compositing (one pass up to 72 channels; wider colours are split, geometry comes from the first pass).

@@ -131,6 +131,26 @@ def test_sync_free_capacity_follows_the_count_one_step_late(cuda_dev, sync_free)
         assert torch.equal(a, b)
 
 
+def test_sync_free_as_a_call_argument(cuda_dev):
+    from gsplat.cuda import _wrapper as W
+    from gsplat.rendering import rasterization
+    assert not W.SYNC_FREE
+    W._ISECT_CAPACITY.clear()
+    cfg, gs, vm, Ks = small_scene(n=3000, w=128, h=80)
+    vm, Ks = vm.to(cuda_dev), Ks.to(cuda_dev)
+    kw = dict(sh_degree=3, packed=False, render_mode="RGB+ED", rasterize_mode="antialiased", return_depth_normal=True)
+    ref = rasterization(*_leaves(gs, cuda_dev), vm, Ks, 128, 80, **kw)
+    assert not W._ISECT_CAPACITY                                    # the default call leaves no state behind
+    rasterization(*_leaves(gs, cuda_dev), vm, Ks, 128, 80, sync_free=True, **kw)
+    got = rasterization(*_leaves(gs, cuda_dev), vm, Ks, 128, 80, sync_free=True, **kw)
+    try:
+        assert torch.is_tensor(got[5]["n_isects"]) and int(got[5]["n_isects"]) == ref[5]["n_isects"]
+        for a, b in zip(got[:5], ref[:5]):
+            assert torch.equal(a, b)
+    finally:
+        W._ISECT_CAPACITY.clear()
+
+
 def test_sync_free_nothing_visible(cuda_dev, sync_free):
     cfg, gs, vm, Ks = small_scene(n=500, w=64, h=48)
     gs["means"] = gs["means"] + 100.0                              # everything behind / outside
