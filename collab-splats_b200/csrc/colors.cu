@@ -34,20 +34,26 @@ __device__ __forceinline__ void camera_position(const float* __restrict__ vm, fl
 // The flat index -> (row, column) split is a division by `row`: ROW > 0 makes it a compile-time constant
 // (K = 16 -> 48 floats, the sh3 case that carries the bandwidth), ROW == 0 keeps the generic run-time form.
 template <int ROW>
-__device__ __forceinline__ void rows_to_smem_t(float* s, const float* __restrict__ src, int count, int row_rt, int RS,
+__device__ __forceinline__ void rows_to_smem_t(float* s, const float* __restrict__ src, int count, int row_rt, int RS_rt,
                                                int t) {
   const int row = ROW > 0 ? ROW : row_rt;
+  const int RS = ROW > 0 ? (ROW | 1) : RS_rt;
   const int total = count * row;
   if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     for (int i = t; i < total / 4; i += CB) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
       const float vv[4] = {v.x, v.y, v.z, v.w};
-      const int f0 = i * 4, r0 = f0 / row, c0 = f0 - r0 * row;   // one division per 16 bytes; row % 4 == 0 or wrap below
+      const int f0 = i * 4, r0 = f0 / row, c0 = f0 - r0 * row;   // one division per 16 bytes
+      if constexpr (ROW > 0 && ROW % 4 == 0) {                   // a 16-byte piece never straddles two rows
+        float* d = s + r0 * RS + c0;
+        d[0] = vv[0]; d[1] = vv[1]; d[2] = vv[2]; d[3] = vv[3];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        int r = r0, c = c0 + k;
-        if (c >= row) { c -= row; ++r; }
-        s[r * RS + c] = vv[k];
+        for (int k = 0; k < 4; ++k) {
+          int r = r0, c = c0 + k;
+          if (c >= row) { c -= row; ++r; }
+          s[r * RS + c] = vv[k];
+        }
       }
     }
   } else {
@@ -55,19 +61,25 @@ __device__ __forceinline__ void rows_to_smem_t(float* s, const float* __restrict
   }
 }
 template <int ROW>
-__device__ __forceinline__ void smem_to_rows_t(const float* s, float* __restrict__ dst, int count, int row_rt, int RS,
+__device__ __forceinline__ void smem_to_rows_t(const float* s, float* __restrict__ dst, int count, int row_rt, int RS_rt,
                                                int t) {
   const int row = ROW > 0 ? ROW : row_rt;
+  const int RS = ROW > 0 ? (ROW | 1) : RS_rt;
   const int total = count * row;
   if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     for (int i = t; i < total / 4; i += CB) {
       float vv[4];
       const int f0 = i * 4, r0 = f0 / row, c0 = f0 - r0 * row;
+      if constexpr (ROW > 0 && ROW % 4 == 0) {
+        const float* d = s + r0 * RS + c0;
+        vv[0] = d[0]; vv[1] = d[1]; vv[2] = d[2]; vv[3] = d[3];
+      } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        int r = r0, c = c0 + k;
-        if (c >= row) { c -= row; ++r; }
-        vv[k] = s[r * RS + c];
+        for (int k = 0; k < 4; ++k) {
+          int r = r0, c = c0 + k;
+          if (c >= row) { c -= row; ++r; }
+          vv[k] = s[r * RS + c];
+        }
       }
       reinterpret_cast<float4*>(dst)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
