@@ -778,6 +778,59 @@ def run_config4(args, device, rank, world, lib, backend):
     return out
 
 
+def run_config3(device, lib, backend, steps=10):
+    """BASELINE config 3: one rade-features training step (collab_splats/models/rade_features_model.py:390-478,564-582) --
+    500 k Gaussians with 3 + 64 channels (+ depth) rendered at 960x540, L1 + depth-normal loss on the rgb part, feature
+    decode (64 -> 64 -> 768 / 384 channels at 38x68) + cosine loss on the feature part, backward."""
+    from gsplat.rendering import rasterization
+    from radegs_b200 import feature_decode as fd, scenes
+    from radegs_b200.losses import fused_rade_loss
+    cfg = scenes.BASELINE_CONFIGS[3]
+    NF = cfg.n_features
+    gs, vm, Ks = scenes.make_scene(cfg, n_views=1)
+    p = [t.to(device).requires_grad_(True) for t in scenes.activate(gs, None)]
+    vmd, Kd = vm.to(device), Ks.to(device)
+    H, W = cfg.height, cfg.width
+    dims = {"clip": (768, 38, 68), "dino": (384, 38, 68)}
+    g = torch.Generator(device=device).manual_seed(cfg.seed)
+    dec = fd.TwoLayerMLP(NF, 64, dims).to(device)
+    gt_feat = {k: torch.randn(*v, device=device, generator=g) for k, v in dims.items()}
+    gt_rgb = torch.randint(0, 256, (H, W, 3), device=device, dtype=torch.uint8, generator=g)
+    fx, fy = float(Ks[0, 0, 0]), float(Ks[0, 1, 1])
+
+    def step():
+        for t in p:
+            t.grad = None
+        for q in dec.parameters():
+            q.grad = None
+        render, alpha, exp_d, med_d, nrm, meta = rasterization(
+            *p, vmd, Kd, W, H, packed=False, render_mode="RGB+ED", rasterize_mode="antialiased", return_depth_normal=True)
+        r = render.view(H, W, -1)
+        loss, _ = fused_rade_loss(r, alpha.view(H, W), exp_d.view(H, W), med_d.view(H, W), nrm.view(H, W, 3), gt_rgb, fx, fy)
+        loss = loss + fd.features_loss(r, dec, dims, "clip", gt_feat, ch0=3, n_features=NF)
+        loss.backward()
+        return meta
+
+    for _ in range(3):
+        meta = step()
+    ms = time_region(step, steps, 1, device) / steps
+    lib.rs_timing_enable(1)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize(device)
+    spans = backend.timing_collect()
+    lib.rs_timing_enable(0)
+    st = {k: round(v[0] / 3, 4) for k, v in sorted(spans.items(), key=lambda kv: -kv[1][0])}
+    out = {"workload": f"BASELINE config 3: rade-features step, {cfg.n_gaussians} Gaussians, 3 + {NF} channels + depth = "
+                       f"{3 + NF + 1} rows, {W}x{H}, RGB+ED antialiased, L1 + depth-normal loss on rgb, feature decode "
+                       "(64 -> 64 -> 768 / 384 channels at 38x68) + cosine loss, backward",
+           "ms_per_step": round(ms, 4), "views_per_s": round(1e3 / ms, 1), "n_isects": int(meta["n_isects"]),
+           "stage_ms": dict(list(st.items())[:12]), "sum_of_library_kernels_ms": round(sum(st.values()), 4)}
+    del p, dec
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_config5(device, lib, backend, n_views=300):
     """BASELINE config 5: the meshing render sweep -- 2 M Gaussians, 300 views at 1080p, forward only, RGB+ED
     (collab_splats/utils/mesh.py:1573-1630) -- once with the outputs left on the device and once the way the reference
@@ -1073,6 +1126,7 @@ def main():
         if rank == 0:
             line["config4"] = c4
             if world == 1:
+                line["config3"] = run_config3(device, lib, backend)
                 line["config5"] = run_config5(device, lib, backend)
                 if not args.no_cpu_baseline:
                     line["config1_cpu_gpu_pair"] = cfg1_pair(device)

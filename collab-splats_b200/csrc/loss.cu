@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(LB) rade_loss_kernel(const LossArgs a) {
       vr[k] = g;
       v_alpha -= g * bg;
     }
-    for (int k = 3; k < a.D; ++k) vr[k] = 0.f;
+    if (a.D <= 8)   // (wider rows -- rade-features -- are zero-filled by one memset before the launch)
+      for (int k = 3; k < a.D; ++k) vr[k] = 0.f;
     a.v_alphas[p] = v_alpha;
     V3 vN = {0.f, 0.f, 0.f};
     if (a.use_dn) {
@@ -109,6 +110,10 @@ extern "C" int rs_rade_loss_fwd_bwd(const float* render, const float* alphas, co
     return RS_ERR_BAD_ARG;
   LossArgs a{render, alphas, exp_depth, med_depth, normals, gt_rgb_u8, background, fx, fy, width, height, D,
              w_l1, w_exp, w_med, use_depth_normal, sums, v_render, v_alphas, v_exp_depth, v_med_depth, v_normals};
+  if (D > 8) {   // the gradient of the non-rgb channels is zero: 4 D bytes per pixel are cheaper to memset than to store
+    cudaError_t e = cudaMemsetAsync(v_render, 0, sizeof(float) * (size_t)width * height * D, (cudaStream_t)stream);
+    if (e != cudaSuccess) { rs_set_last_cuda_error((int)e); return RS_ERR_LAUNCH; }
+  }
   dim3 grid(rs_div_up(width, 32), rs_div_up(height, 8));
   rade_loss_kernel<<<grid, LB, 0, (cudaStream_t)stream>>>(a);
   RS_RETURN_LAST_ERROR();

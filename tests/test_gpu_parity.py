@@ -623,7 +623,7 @@ def test_full_view_matches_c_oracle(cuda_dev, cfg_id):
 
 
 # ------------------------------------------------------------------------------------------------ fused loss (8f row f1)
-@pytest.mark.parametrize("use_dn,with_bg,D", [(True, False, 4), (True, True, 3), (False, False, 3)])
+@pytest.mark.parametrize("use_dn,with_bg,D", [(True, False, 4), (True, True, 3), (False, False, 3), (True, False, 12)])
 def test_fused_loss_matches_reference_glue(cuda_dev, use_dn, with_bg, D):
     """csrc/loss.cu against the reference's own post-render arithmetic (camera_utils.py:176-279,
     rade_gs_model.py:202-219,292-307) restated in torch (radegs_b200.losses / the oracle)."""
