@@ -201,3 +201,87 @@ def test_render_modes_and_antialiasing():
     aa = O.rasterization(*p, vm, Ks, 64, 48, sh_degree=2, rasterize_mode="antialiased")
     assert float(aa[1].mean()) < float(rgb[1].mean())      # compensation only ever lowers opacity
     assert torch.equal(aa[2]["isect_ids"], rgb[2]["isect_ids"])
+
+
+@pytest.mark.parametrize("compositor", ["torch", "c"])
+@pytest.mark.parametrize("front_first_in_memory", [True, False])
+def test_two_gaussian_stack_closed_form(compositor, front_first_in_memory):
+    """Two isotropic Gaussians on the optical axis at depths 3 and 5: the centre pixel is the textbook front-to-back
+    composite  C = a1 c1 + (1 - a1) a2 c2,  alpha = 1 - (1 - a1)(1 - a2),  expected depth = (a1 t1 + (1 - a1) a2 t2) / |ray|,
+    expected normal = -(a1 + (1 - a1) a2) z,  and the median depth is that of the Gaussian under which the transmittance
+    first falls below 1/2 -- whatever the order of the two in memory (sorted by depth), for both compositors."""
+    dt = torch.float64
+    W = H = 32
+    f = 80.0
+    vm = torch.eye(4, dtype=dt)[None].clone()                       # camera at the origin looking down +z
+    Ks = torch.tensor([[[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]]], dtype=dt)
+    z = [3.0, 5.0]
+    s = [0.15, 0.4]
+    o = [0.4, 0.8]
+    c = [[0.9, 0.1, 0.2], [0.1, 0.7, 0.3]]
+    order = [0, 1] if front_first_in_memory else [1, 0]
+    means = torch.tensor([[0.0, 0.0, z[i]] for i in order], dtype=dt)
+    quats = torch.tensor([[1.0, 0, 0, 0]] * 2, dtype=dt)
+    scales = torch.tensor([[s[i]] * 3 for i in order], dtype=dt)
+    opac = torch.tensor([o[i] for i in order], dtype=dt)
+    cols = torch.tensor([c[i] for i in order], dtype=dt)
+    kw = dict(compositor=compositor) if compositor == "c" else {}
+    rc, ra, de, dm, nr, meta = O.rasterization(means, quats, scales, opac, cols, vm, Ks, W, H, return_depth_normal=True,
+                                               **kw)
+    # pixel (15,15): centre (15.5,15.5), offset (0.5,0.5) px from both projected means (16,16)
+    a = []
+    for i in range(2):
+        sig2 = (f * s[i] / z[i]) ** 2 + 0.3                         # projected variance + the 0.3 px^2 blur
+        a.append(min(0.99, o[i] * math.exp(-0.5 * (0.25 + 0.25) / sig2)))
+    a1, a2 = a
+    ln = math.sqrt(2 * (0.5 / f) ** 2 + 1)                          # |ray| through the pixel centre, z = 1
+    # ray distance t of a fronto-parallel isotropic Gaussian at the pixel: the ray-space plane through its centre
+    vis = [a1, (1 - a1) * a2]
+    assert abs(ra[0, 15, 15, 0].item() - (1 - (1 - a1) * (1 - a2))) < 1e-12
+    want_c = vis[0] * torch.tensor(c[0], dtype=dt) + vis[1] * torch.tensor(c[1], dtype=dt)
+    assert torch.allclose(rc[0, 15, 15], want_c, atol=1e-12)
+    assert torch.allclose(nr[0, 15, 15], torch.tensor([0.0, 0.0, -(vis[0] + vis[1])], dtype=dt), atol=1e-9)
+    assert abs(de[0, 15, 15, 0].item() - (vis[0] * z[0] + vis[1] * z[1]) / ln) < 1e-6
+    # T after the front Gaussian is 1 - a1 = 0.6+ > 1/2, after the back one (1 - a1)(1 - a2) < 1/2: median = the back one
+    assert (1 - a1) > 0.5 > (1 - a1) * (1 - a2)
+    assert abs(dm[0, 15, 15, 0].item() - z[1] / ln) < 1e-6
+    # the tile lists are depth-ordered: front Gaussian first, whatever the memory order
+    ids = meta["flatten_ids"]
+    first = int(ids[0])
+    assert first == order.index(0)
+
+
+def _real_sh_reference(l, m, x, y, z):
+    """Real spherical harmonics from the textbook Cartesian forms, written independently of the oracle (normalisation
+    constants from the factorial formula N_lm = sqrt((2l+1)/(4 pi) (l-|m|)!/(l+|m|)!))."""
+    def N(l_, m_):
+        return math.sqrt((2 * l_ + 1) / (4 * math.pi) * math.factorial(l_ - abs(m_)) / math.factorial(l_ + abs(m_)))
+    r2 = math.sqrt(2.0)
+    table = {
+        (0, 0): N(0, 0),
+        (1, -1): r2 * N(1, 1) * y, (1, 0): N(1, 0) * z, (1, 1): r2 * N(1, 1) * x,
+        (2, -2): r2 * N(2, 2) * 3 * (2 * x * y), (2, -1): r2 * N(2, 1) * 3 * y * z,
+        (2, 0): N(2, 0) * 0.5 * (3 * z * z - 1), (2, 1): r2 * N(2, 1) * 3 * x * z,
+        (2, 2): r2 * N(2, 2) * 3 * (x * x - y * y),
+        (3, -3): r2 * N(3, 3) * 15 * y * (3 * x * x - y * y), (3, -2): r2 * N(3, 2) * 15 * (2 * x * y) * z,
+        (3, -1): r2 * N(3, 1) * 1.5 * y * (5 * z * z - 1), (3, 0): N(3, 0) * 0.5 * z * (5 * z * z - 3),
+        (3, 1): r2 * N(3, 1) * 1.5 * x * (5 * z * z - 1), (3, 2): r2 * N(3, 2) * 15 * (x * x - y * y) * z,
+        (3, 3): r2 * N(3, 3) * 15 * x * (x * x - 3 * y * y),
+    }
+    return table[(l, m)]
+
+
+def test_sh_basis_is_the_real_spherical_harmonics_up_to_the_3dgs_sign_convention():
+    """The oracle's basis (gsplat ordering k = l^2 + l + m) against textbook real SH evaluated independently: equal up to
+    the Condon-Shortley-free sign (-1)^m that the 3DGS code base uses for odd m (Y_1^{+-1}, Y_2^{+-1}, Y_3^{+-1,+-3})."""
+    g = torch.Generator().manual_seed(5)
+    dirs = torch.nn.functional.normalize(torch.randn(7, 3, generator=g, dtype=torch.float64), dim=-1)
+    for l in range(4):
+        for m in range(-l, l + 1):
+            k = l * l + l + m
+            coeffs = torch.zeros(7, 16, 3, dtype=torch.float64)
+            coeffs[:, k, :] = 1.0
+            got = O.spherical_harmonics(3, dirs, coeffs)[:, 0]
+            want = torch.tensor([_real_sh_reference(l, m, *d.tolist()) for d in dirs], dtype=torch.float64)
+            sign = -1.0 if (m % 2 != 0) else 1.0
+            assert torch.allclose(got, sign * want, atol=1e-12), (l, m, got[:3], want[:3])
